@@ -1,0 +1,555 @@
+// C ABI of libdmi_b200.so (see include/dmi_b200.h).  Host-side orchestration only: contexts, device
+// buffers, the double-buffered host->device view pipeline, chunking of views into kernel launches.
+// Everything numeric happens in tsdf_kernels.cu / color_kernels.cu; there is no CPU fallback.
+#include "../../include/dmi_b200.h"
+#include "dmi_internal.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct EventSpan { cudaEvent_t a, b; };
+
+struct KernelStats
+{
+  std::vector<EventSpan> pending;
+  std::vector<EventSpan> pool;
+  long long launches = 0;
+  EventSpan open() {
+    EventSpan s;
+    if (!pool.empty()) { s = pool.back(); pool.pop_back(); }
+    else { cudaEventCreate(&s.a); cudaEventCreate(&s.b); }
+    return s;
+  }
+  float drain() {
+    float total = 0.f;
+    for (auto& s : pending) { float ms = 0.f; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) total += ms; pool.push_back(s); }
+    pending.clear();
+    return total;
+  }
+  void destroy() {
+    for (auto& s : pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto& s : pool) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    pending.clear(); pool.clear();
+  }
+};
+
+}  // namespace
+
+struct dmi_ctx
+{
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  bool initialized = false;
+  dmi::GridParams g{};
+  // volume slab
+  DevBuf vol;
+  size_t vol_bytes = 0;
+  int vol_type = DMI_F64;
+  bool vol_active = false;
+  // host-view pipeline: two staging slots
+  DevBuf stage_depth[2], stage_cost[2], filtered;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false};
+  // coloration scratch
+  DevBuf c_xyz, c_colors, c_mats, c_mean, c_median, c_nb;
+  KernelStats tsdf_stats, color_stats;
+  long long opt_kernel = DMI_TSDF_KERNEL_AUTO, opt_chunk = 0;
+  long long total_launches = 0;
+  std::string err;
+
+  int fail(int code, const std::string& msg) { err = msg; return code; }
+  int fail_cuda(cudaError_t e, const char* what)
+  {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? DMI_ERR_OUT_OF_MEMORY : DMI_ERR_CUDA;
+  }
+};
+
+#define DMI_CK(call)                                                       \
+  do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ctx->fail_cuda(e__, #call); } while (0)
+#define DMI_REQUIRE(cond, msg)                                             \
+  do { if (!(cond)) return ctx->fail(DMI_ERR_INVALID_ARGUMENT, msg); } while (0)
+
+extern "C" {
+
+int dmi_abi_version(void) { return DMI_ABI_VERSION; }
+
+int dmi_device_count(int* count)
+{
+  if (!count) return DMI_ERR_INVALID_ARGUMENT;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) { *count = 0; g_create_error = cudaGetErrorString(e); cudaGetLastError(); return DMI_ERR_CUDA; }
+  return DMI_OK;
+}
+
+int dmi_create(int device, dmi_ctx** out)
+{
+  if (!out) return DMI_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+  {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return DMI_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { g_create_error = "device index out of range"; return DMI_ERR_INVALID_ARGUMENT; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return DMI_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return DMI_ERR_CUDA; }
+  if (prop.major != 10)
+  {
+    g_create_error = "libdmi_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return DMI_ERR_CUDA;
+  }
+  dmi_ctx* ctx = new dmi_ctx();
+  ctx->device = device;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+  {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return DMI_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  for (int b = 0; b < 2; b++)
+  {
+    cudaEventCreateWithFlags(&ctx->ev_ready[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming);
+  }
+  *out = ctx;
+  return DMI_OK;
+}
+
+int dmi_destroy(dmi_ctx* ctx)
+{
+  if (!ctx) return DMI_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  ctx->vol.release();
+  for (int b = 0; b < 2; b++)
+  {
+    ctx->stage_depth[b].release(); ctx->stage_cost[b].release();
+    if (ctx->ev_ready[b]) cudaEventDestroy(ctx->ev_ready[b]);
+    if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
+  }
+  ctx->filtered.release();
+  ctx->c_xyz.release(); ctx->c_colors.release(); ctx->c_mats.release();
+  ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release();
+  ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
+  cudaStreamDestroy(ctx->own_stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return DMI_OK;
+}
+
+const char* dmi_last_error(const dmi_ctx* ctx)
+{
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int dmi_set_stream(dmi_ctx* ctx, void* cuda_stream)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return DMI_OK;
+}
+
+int dmi_synchronize(dmi_ctx* ctx)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(cudaStreamSynchronize(ctx->copy_stream));
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  return DMI_OK;
+}
+
+int dmi_set_option(dmi_ctx* ctx, int option, long long value)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  switch (option)
+  {
+    case DMI_OPT_TSDF_KERNEL:
+      DMI_REQUIRE(value == DMI_TSDF_KERNEL_AUTO || value == DMI_TSDF_KERNEL_EXACT, "unknown TSDF kernel id");
+      ctx->opt_kernel = value; return DMI_OK;
+    case DMI_OPT_VIEW_CHUNK:
+      DMI_REQUIRE(value >= 0, "view chunk must be >= 0");
+      ctx->opt_chunk = value; return DMI_OK;
+    default:
+      return ctx->fail(DMI_ERR_INVALID_ARGUMENT, "unknown option");
+  }
+}
+
+// ---- TSDF -------------------------------------------------------------------------------------
+
+int dmi_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims[3],
+                   const double gridOrig[3], const double gridSpacing[3],
+                   double thick, double rho, double eta, double delta, const int depthMapDims[2])
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_REQUIRE(gridMatrix && gridDims && gridOrig && gridSpacing && depthMapDims, "null argument");
+  DMI_REQUIRE(gridDims[0] >= 2 && gridDims[1] >= 2 && gridDims[2] >= 2, "grid point dims must be >= 2 (at least one cell)");
+  DMI_REQUIRE(depthMapDims[0] >= 1 && depthMapDims[1] >= 1, "depth map dims must be >= 1");
+  DMI_REQUIRE((long long)depthMapDims[0] * depthMapDims[1] < (1ll << 31), "depth map too large for the reference's int pixel index");
+  // the one parameter combination the reference filter rejects (vtkCudaReconstructionFilter.cxx:138-142)
+  if (rho == 0 && thick == 0) return ctx->fail(DMI_ERR_BAD_PARAMETERS, "Ray potential Rho or Thickness or both have not been set");
+  dmi::GridParams& g = ctx->g;
+  memcpy(g.gm, gridMatrix, sizeof(double) * 12);
+  for (int a = 0; a < 3; a++) { g.orig[a] = gridOrig[a]; g.sp[a] = gridSpacing[a]; }
+  g.Nx = gridDims[0] - 1; g.Ny = gridDims[1] - 1; g.Nz = gridDims[2] - 1;
+  g.k0 = 0; g.k1 = g.Nz;
+  g.W = depthMapDims[0]; g.H = depthMapDims[1];
+  g.thick = thick; g.rho = rho; g.eta = eta; g.delta = delta;
+  g.rho_over_thick = rho / thick;
+  g.neg_eta_rho = -eta * rho;
+  ctx->initialized = true;
+  ctx->vol_active = false;
+  return DMI_OK;
+}
+
+int dmi_set_slab(dmi_ctx* ctx, int k0, int k1)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  DMI_REQUIRE(0 <= k0 && k0 <= k1 && k1 <= ctx->g.Nz, "slab must satisfy 0 <= k0 <= k1 <= Nz");
+  ctx->g.k0 = k0; ctx->g.k1 = k1;
+  ctx->vol_active = false;
+  return DMI_OK;
+}
+
+static size_t slab_cells(const dmi::GridParams& g)
+{
+  return (size_t)g.Nx * g.Ny * (size_t)(g.k1 - g.k0);
+}
+
+int dmi_volume_begin(dmi_ctx* ctx, const void* h_scalar, int scalarType)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  DMI_REQUIRE(scalarType == DMI_F32 || scalarType == DMI_F64, "scalarType must be DMI_F32 or DMI_F64");
+  DMI_CK(cudaSetDevice(ctx->device));
+  const size_t bytes = slab_cells(ctx->g) * (scalarType == DMI_F64 ? 8 : 4);
+  DMI_CK(ctx->vol.ensure(bytes > 0 ? bytes : 8));
+  ctx->vol_bytes = bytes;
+  ctx->vol_type = scalarType;
+  if (bytes)
+  {
+    if (h_scalar) DMI_CK(cudaMemcpyAsync(ctx->vol.p, h_scalar, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else DMI_CK(cudaMemsetAsync(ctx->vol.p, 0, bytes, ctx->stream));
+  }
+  ctx->vol_active = true;
+  return DMI_OK;
+}
+
+// Launches the integration kernels for nViews views whose (already filtered) depth maps sit at d_depths.
+static int integrate_resident(dmi_ctx* ctx, int nViews, const double* d_depths, const double* K, const double* RT)
+{
+  const dmi::GridParams& g = ctx->g;
+  if (slab_cells(g) == 0) return DMI_OK;
+  const size_t npix = (size_t)g.W * g.H;
+  EventSpan span = ctx->tsdf_stats.open();
+  DMI_CK(cudaEventRecord(span.a, ctx->stream));
+  int chunk = dmi::kExactChunk;
+  if (ctx->opt_chunk > 0 && ctx->opt_chunk < chunk) chunk = (int)ctx->opt_chunk;
+  for (int v0 = 0; v0 < nViews; v0 += chunk)
+  {
+    dmi::ExactChunk c;
+    c.n = std::min(chunk, nViews - v0);
+    c.pad = 0;
+    for (int q = 0; q < c.n; q++)
+    {
+      memcpy(c.v[q].RT, RT + 16 * (size_t)(v0 + q), sizeof(double) * 12);
+      memcpy(c.v[q].K, K + 16 * (size_t)(v0 + q), sizeof(double) * 12);
+    }
+    DMI_CK(dmi::launch_tsdf_exact(g, c, d_depths + npix * v0, ctx->vol.p, ctx->vol_type, ctx->stream));
+    ctx->tsdf_stats.launches++;
+    ctx->total_launches++;
+  }
+  DMI_CK(cudaEventRecord(span.b, ctx->stream));
+  ctx->tsdf_stats.pending.push_back(span);
+  return DMI_OK;
+}
+
+int dmi_volume_integrate_device(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
+                                double thresholdBestCost, const double* K, const double* RT)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized || !ctx->vol_active) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_volume_begin has not been called");
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
+  DMI_REQUIRE(d_depths && K && RT, "null argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  const size_t npix = (size_t)ctx->g.W * ctx->g.H;
+  if (!d_bestCost) return integrate_resident(ctx, nViews, d_depths, K, RT);
+  // The caller's depth buffer is const: filter into scratch, a bounded number of views at a time.
+  const int step = (int)std::max<size_t>(1, std::min<size_t>((size_t)nViews, (512ull << 20) / (npix * 8)));
+  DMI_CK(ctx->filtered.ensure((size_t)step * npix * 8));
+  for (int v0 = 0; v0 < nViews; v0 += step)
+  {
+    const int n = std::min(step, nViews - v0);
+    DMI_CK(cudaMemcpyAsync(ctx->filtered.p, d_depths + npix * v0, (size_t)n * npix * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    DMI_CK(dmi::launch_depth_threshold((double*)ctx->filtered.p, d_bestCost + npix * v0, (size_t)n * npix, thresholdBestCost, ctx->stream));
+    ctx->total_launches++;
+    int rc = integrate_resident(ctx, n, (const double*)ctx->filtered.p, K + 16 * (size_t)v0, RT + 16 * (size_t)v0);
+    if (rc != DMI_OK) return rc;
+  }
+  return DMI_OK;
+}
+
+int dmi_volume_integrate_host(dmi_ctx* ctx, int nViews, const double* depths, const double* bestCost,
+                              double thresholdBestCost, const double* K, const double* RT)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized || !ctx->vol_active) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_volume_begin has not been called");
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
+  DMI_REQUIRE(depths && K && RT, "null argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  const size_t npix = (size_t)ctx->g.W * ctx->g.H;
+  // staging slot = as many views as fit in 256 MB, at least 1, at most 64
+  const int step = (int)std::max<size_t>(1, std::min<size_t>(64, (256ull << 20) / (npix * 8)));
+  int slot = 0;
+  for (int v0 = 0; v0 < nViews; v0 += step, slot ^= 1)
+  {
+    const int n = std::min(step, nViews - v0);
+    const size_t bytes = (size_t)n * npix * 8;
+    DMI_CK(ctx->stage_depth[slot].ensure((size_t)step * npix * 8));
+    if (bestCost) DMI_CK(ctx->stage_cost[slot].ensure((size_t)step * npix * 8));
+    // the copy engine may only overwrite the slot once the kernels that read it are done
+    if (ctx->slot_used[slot]) DMI_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));
+    DMI_CK(cudaMemcpyAsync(ctx->stage_depth[slot].p, depths + npix * v0, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (bestCost)
+      DMI_CK(cudaMemcpyAsync(ctx->stage_cost[slot].p, bestCost + npix * v0, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    DMI_CK(cudaEventRecord(ctx->ev_ready[slot], ctx->copy_stream));
+    DMI_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[slot], 0));
+    if (bestCost)
+    {
+      DMI_CK(dmi::launch_depth_threshold((double*)ctx->stage_depth[slot].p, (const double*)ctx->stage_cost[slot].p,
+                                         (size_t)n * npix, thresholdBestCost, ctx->stream));
+      ctx->total_launches++;
+    }
+    int rc = integrate_resident(ctx, n, (const double*)ctx->stage_depth[slot].p, K + 16 * (size_t)v0, RT + 16 * (size_t)v0);
+    if (rc != DMI_OK) return rc;
+    DMI_CK(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
+    ctx->slot_used[slot] = true;
+  }
+  // host pointers: synchronous at the ABI
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  return DMI_OK;
+}
+
+int dmi_volume_end(dmi_ctx* ctx, void* h_scalar)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized || !ctx->vol_active) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_volume_begin has not been called");
+  DMI_CK(cudaSetDevice(ctx->device));
+  if (h_scalar && ctx->vol_bytes)
+    DMI_CK(cudaMemcpyAsync(h_scalar, ctx->vol.p, ctx->vol_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  return DMI_OK;
+}
+
+int dmi_volume_device_ptr(dmi_ctx* ctx, void** d_ptr, size_t* bytes)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized || !ctx->vol_active) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_volume_begin has not been called");
+  if (d_ptr) *d_ptr = ctx->vol.p;
+  if (bytes) *bytes = ctx->vol_bytes;
+  return DMI_OK;
+}
+
+int dmi_process_depth_maps(dmi_ctx* ctx, int nViews, const double* depths, const double* bestCost,
+                           double thresholdBestCost, const double* K, const double* RT,
+                           void* io_scalar, int scalarType)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
+  DMI_REQUIRE(depths && K && RT && io_scalar, "null argument");
+  int rc = dmi_volume_begin(ctx, io_scalar, scalarType);
+  if (rc != DMI_OK) return rc;
+  rc = dmi_volume_integrate_host(ctx, nViews, depths, bestCost, thresholdBestCost, K, RT);
+  if (rc != DMI_OK) return rc;
+  return dmi_volume_end(ctx, io_scalar);
+}
+
+int dmi_apply_depth_threshold_device(dmi_ctx* ctx, size_t count, double* d_depths, const double* d_bestCost,
+                                     double thresholdBestCost)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_REQUIRE(count == 0 || (d_depths && d_bestCost), "null argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(dmi::launch_depth_threshold(d_depths, d_bestCost, count, thresholdBestCost, ctx->stream));
+  if (count) ctx->total_launches++;
+  return DMI_OK;
+}
+
+int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  if (ms) *ms = ctx->tsdf_stats.drain(); else ctx->tsdf_stats.drain();
+  if (launches) *launches = ctx->tsdf_stats.launches;
+  ctx->tsdf_stats.launches = 0;
+  return DMI_OK;
+}
+
+// ---- coloration ---------------------------------------------------------------------------------
+
+static int pack_color_views(dmi_ctx* ctx, int nViews, const double* K, const double* RT, dmi::ColorViews* out)
+{
+  const int stride = (nViews + 31) & ~31;
+  std::vector<double> m((size_t)21 * stride, 0.0);
+  for (int v = 0; v < nViews; v++)
+  {
+    for (int e = 0; e < 12; e++) m[(size_t)e * stride + v] = RT[16 * (size_t)v + e];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) m[(size_t)(12 + r * 3 + c) * stride + v] = K[16 * (size_t)v + r * 4 + c];
+  }
+  DMI_CK(ctx->c_mats.ensure(m.size() * 8));
+  // pageable source: the copy has consumed `m` by the time cudaMemcpyAsync returns
+  DMI_CK(cudaMemcpyAsync(ctx->c_mats.p, m.data(), m.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  out->m = (const double*)ctx->c_mats.p;
+  out->nViews = nViews;
+  out->stride = stride;
+  return DMI_OK;
+}
+
+int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyzType, int nViews,
+                        const uint8_t* d_colors, const double* K, const double* RT, int W, int H,
+                        uint8_t* d_mean, uint8_t* d_median, int32_t* d_nb)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  // MeshColoration::ProcessColoration returns false without views (MeshColoration.cxx:102-106)
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "Error when input has been set or during reading vti/krtd file path");
+  DMI_REQUIRE(xyzType == DMI_F32 || xyzType == DMI_F64, "xyzType must be DMI_F32 or DMI_F64");
+  DMI_REQUIRE(W >= 1 && H >= 1, "image dims must be >= 1");
+  DMI_REQUIRE(K && RT, "null argument");
+  if (nPoints == 0) return DMI_OK;
+  DMI_REQUIRE(d_xyz && d_colors && d_mean && d_median && d_nb, "null argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  dmi::ColorViews views;
+  int rc = pack_color_views(ctx, nViews, K, RT, &views);
+  if (rc != DMI_OK) return rc;
+  EventSpan span = ctx->color_stats.open();
+  DMI_CK(cudaEventRecord(span.a, ctx->stream));
+  DMI_CK(dmi::launch_colorize(nPoints, d_xyz, xyzType, views, d_colors, W, H, d_mean, d_median, d_nb, ctx->stream));
+  DMI_CK(cudaEventRecord(span.b, ctx->stream));
+  ctx->color_stats.pending.push_back(span);
+  ctx->color_stats.launches++;
+  ctx->total_launches++;
+  return DMI_OK;
+}
+
+int dmi_colorize(dmi_ctx* ctx, size_t nPoints, const void* xyz, int xyzType, int nViews,
+                 const uint8_t* colors, const double* K, const double* RT, int W, int H,
+                 uint8_t* mean, uint8_t* median, int32_t* nbProjected)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "Error when input has been set or during reading vti/krtd file path");
+  DMI_REQUIRE(xyzType == DMI_F32 || xyzType == DMI_F64, "xyzType must be DMI_F32 or DMI_F64");
+  DMI_REQUIRE(W >= 1 && H >= 1, "image dims must be >= 1");
+  DMI_REQUIRE(K && RT && colors, "null argument");
+  if (nPoints == 0) return DMI_OK;
+  DMI_REQUIRE(xyz && mean && median && nbProjected, "null argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  const size_t xyzBytes = nPoints * 3 * (xyzType == DMI_F64 ? 8 : 4);
+  const size_t colBytes = (size_t)nViews * W * H * 3;
+  DMI_CK(ctx->c_xyz.ensure(xyzBytes));
+  DMI_CK(ctx->c_colors.ensure(colBytes));
+  DMI_CK(ctx->c_mean.ensure(nPoints * 3));
+  DMI_CK(ctx->c_median.ensure(nPoints * 3));
+  DMI_CK(ctx->c_nb.ensure(nPoints * 4));
+  DMI_CK(cudaMemcpyAsync(ctx->c_xyz.p, xyz, xyzBytes, cudaMemcpyHostToDevice, ctx->stream));
+  DMI_CK(cudaMemcpyAsync(ctx->c_colors.p, colors, colBytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = dmi_colorize_device(ctx, nPoints, ctx->c_xyz.p, xyzType, nViews, (const uint8_t*)ctx->c_colors.p, K, RT, W, H,
+                               (uint8_t*)ctx->c_mean.p, (uint8_t*)ctx->c_median.p, (int32_t*)ctx->c_nb.p);
+  if (rc != DMI_OK) return rc;
+  DMI_CK(cudaMemcpyAsync(mean, ctx->c_mean.p, nPoints * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  DMI_CK(cudaMemcpyAsync(median, ctx->c_median.p, nPoints * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  DMI_CK(cudaMemcpyAsync(nbProjected, ctx->c_nb.p, nPoints * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  return DMI_OK;
+}
+
+int dmi_color_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  if (ms) *ms = ctx->color_stats.drain(); else ctx->color_stats.drain();
+  if (launches) *launches = ctx->color_stats.launches;
+  ctx->color_stats.launches = 0;
+  return DMI_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------------
+
+int dmi_launch_counter(dmi_ctx* ctx, long long* launches)
+{
+  if (!ctx || !launches) return DMI_ERR_INVALID_ARGUMENT;
+  *launches = ctx->total_launches;
+  return DMI_OK;
+}
+
+int dmi_measure_fp_peak(dmi_ctx* ctx, int which, double ms_target, double* tflops)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_REQUIRE(tflops && (which == 0 || which == 1) && ms_target > 0, "bad argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  DMI_CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 8;
+  const int iters = 2048;
+  const double flopsPerLaunch = (double)blocks * dmi::kPeakThreads * iters * 8.0 * dmi::kPeakChains * 2.0;
+  DevBuf sink;
+  DMI_CK(sink.ensure(64));
+  cudaEvent_t a, b;
+  DMI_CK(cudaEventCreate(&a)); DMI_CK(cudaEventCreate(&b));
+  for (int w = 0; w < 3; w++) DMI_CK(dmi::launch_fp_peak(which, blocks, iters, (float*)sink.p, ctx->stream));
+  DMI_CK(cudaEventRecord(a, ctx->stream));
+  DMI_CK(dmi::launch_fp_peak(which, blocks, iters, (float*)sink.p, ctx->stream));
+  DMI_CK(cudaEventRecord(b, ctx->stream));
+  DMI_CK(cudaEventSynchronize(b));
+  float one = 0.f;
+  DMI_CK(cudaEventElapsedTime(&one, a, b));
+  int reps = (int)std::max(1.0, std::ceil(ms_target / std::max(one, 1e-3f)));
+  DMI_CK(cudaEventRecord(a, ctx->stream));
+  for (int r = 0; r < reps; r++) DMI_CK(dmi::launch_fp_peak(which, blocks, iters, (float*)sink.p, ctx->stream));
+  DMI_CK(cudaEventRecord(b, ctx->stream));
+  DMI_CK(cudaEventSynchronize(b));
+  float ms = 0.f;
+  DMI_CK(cudaEventElapsedTime(&ms, a, b));
+  *tflops = flopsPerLaunch * reps / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  sink.release();
+  return DMI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""Thin Python handle on one dmi context (= one GPU).  Pointers in, status codes out; numpy arrays are
+passed by address, device buffers as integer addresses (e.g. ``tensor.data_ptr()``)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DMI_F32, DMI_F64, DmiError  # noqa: F401  (re-exported)
+
+
+def _ptr(a):
+    """address of a C-contiguous numpy array, an int device address, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return C.c_void_p(a.ctypes.data)
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def _f64(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_last is not None and a.size % shape_last != 0:
+        raise ValueError("bad array size")
+    return a
+
+
+def scalar_code(dtype) -> int:
+    dt = np.dtype(dtype)
+    if dt == np.float64:
+        return DMI_F64
+    if dt == np.float32:
+        return DMI_F32
+    raise ValueError("scalar type must be float32 or float64 (TVolumetric of ProcessDepthMap<T>)")
+
+
+class Context:
+    """One GPU.  All numeric work happens in libdmi_b200.so; a missing library raises ImportError."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.dmi_create(int(device), C.byref(h))
+        if rc != _lib.DMI_OK:
+            msg = self._lib.dmi_last_error(None)
+            raise DmiError(rc, msg.decode() if msg else "")
+        self._h = h
+        self.device = int(device)
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dmi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        _lib.check(self._h, rc)
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(self._lib.dmi_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        self._ck(self._lib.dmi_synchronize(self._h))
+
+    def set_option(self, option: int, value: int):
+        self._ck(self._lib.dmi_set_option(self._h, int(option), int(value)))
+
+    # -- TSDF ----------------------------------------------------------------------------------
+    def initialize(self, grid_matrix, grid_dims, grid_orig, grid_spacing, thick, rho, eta, delta, depth_map_dims):
+        """CudaInitialize (CudaReconstruction.cu:269-298).  grid_dims are POINT dims."""
+        gm = _f64(grid_matrix).reshape(16)
+        gd = np.ascontiguousarray(grid_dims, dtype=np.int32).reshape(3)
+        go = _f64(grid_orig).reshape(3)
+        gs = _f64(grid_spacing).reshape(3)
+        dd = np.ascontiguousarray(depth_map_dims, dtype=np.int32).reshape(2)
+        self._ck(self._lib.dmi_initialize(self._h, _ptr(gm), _ptr(gd), _ptr(go), _ptr(gs),
+                                          float(thick), float(rho), float(eta), float(delta), _ptr(dd)))
+        self._cells = (int(gd[0]) - 1, int(gd[1]) - 1, int(gd[2]) - 1)
+        self._slab = (0, self._cells[2])
+        self._dd = (int(dd[0]), int(dd[1]))
+
+    def set_slab(self, k0: int, k1: int):
+        self._ck(self._lib.dmi_set_slab(self._h, int(k0), int(k1)))
+        self._slab = (int(k0), int(k1))
+
+    @property
+    def slab_cells(self) -> int:
+        return self._cells[0] * self._cells[1] * (self._slab[1] - self._slab[0])
+
+    def process_depth_maps(self, depths, best_cost, threshold_best_cost, K, RT, io_scalar: np.ndarray):
+        """ProcessDepthMap<T> (CudaReconstruction.cu:302-386) on in-memory views; accumulates onto io_scalar."""
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        n = K.size // 16
+        if RT.size // 16 < n:
+            raise ValueError("not enough RT matrices for the K matrices")
+        depths = _f64(depths)
+        if best_cost is not None:
+            best_cost = _f64(best_cost)
+        if n > 0:
+            npix = self._dd[0] * self._dd[1]
+            if depths.size != n * npix or (best_cost is not None and best_cost.size != n * npix):
+                raise ValueError("depth / best-cost arrays must hold nViews * H * W doubles")
+        if io_scalar.size != self.slab_cells or not io_scalar.flags["C_CONTIGUOUS"]:
+            raise ValueError("io_scalar must be a C-contiguous array of the slab's cells")
+        self._ck(self._lib.dmi_process_depth_maps(self._h, n, _ptr(depths), _ptr(best_cost), float(threshold_best_cost),
+                                                  _ptr(K), _ptr(RT), _ptr(io_scalar), scalar_code(io_scalar.dtype)))
+        return io_scalar
+
+    def volume_begin(self, h_scalar: np.ndarray | None, dtype=np.float64):
+        if h_scalar is not None:
+            dtype = h_scalar.dtype
+            if h_scalar.size != self.slab_cells:
+                raise ValueError("h_scalar must hold the slab's cells")
+        self._vol_dtype = np.dtype(dtype)
+        self._ck(self._lib.dmi_volume_begin(self._h, _ptr(h_scalar), scalar_code(dtype)))
+
+    def volume_integrate_host(self, depths, best_cost, threshold_best_cost, K, RT):
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        depths = _f64(depths)
+        best_cost = None if best_cost is None else _f64(best_cost)
+        self._ck(self._lib.dmi_volume_integrate_host(self._h, K.size // 16, _ptr(depths), _ptr(best_cost),
+                                                     float(threshold_best_cost), _ptr(K), _ptr(RT)))
+
+    def volume_integrate_device(self, n_views: int, d_depths: int, d_best_cost: int | None, threshold_best_cost, K, RT):
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        self._ck(self._lib.dmi_volume_integrate_device(self._h, int(n_views), _ptr(int(d_depths)),
+                                                       _ptr(int(d_best_cost)) if d_best_cost else None,
+                                                       float(threshold_best_cost), _ptr(K), _ptr(RT)))
+
+    def volume_end(self, h_scalar: np.ndarray | None = None):
+        if h_scalar is not None and (h_scalar.size != self.slab_cells or h_scalar.dtype != self._vol_dtype):
+            raise ValueError("h_scalar must match the slab's size and scalar type")
+        self._ck(self._lib.dmi_volume_end(self._h, _ptr(h_scalar)))
+        return h_scalar
+
+    def volume_device_ptr(self):
+        p = C.c_void_p()
+        b = C.c_size_t()
+        self._ck(self._lib.dmi_volume_device_ptr(self._h, C.byref(p), C.byref(b)))
+        return int(p.value or 0), int(b.value)
+
+    def apply_depth_threshold_device(self, count: int, d_depths: int, d_best_cost: int, threshold: float):
+        self._ck(self._lib.dmi_apply_depth_threshold_device(self._h, int(count), _ptr(int(d_depths)),
+                                                            _ptr(int(d_best_cost)), float(threshold)))
+
+    def tsdf_kernel_stats(self):
+        ms = C.c_float()
+        n = C.c_longlong()
+        self._ck(self._lib.dmi_tsdf_kernel_stats(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    # -- coloration ------------------------------------------------------------------------------
+    def colorize(self, xyz: np.ndarray, colors: np.ndarray, K, RT, width: int, height: int):
+        """MeshColoration::ProcessColoration's loop (MeshColoration.cxx:140-192) on in-memory views."""
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        n = K.size // 16
+        xyz = np.ascontiguousarray(xyz)
+        if xyz.dtype not in (np.float32, np.float64):
+            xyz = xyz.astype(np.float64)
+        P = xyz.size // 3
+        colors = np.ascontiguousarray(colors, dtype=np.uint8)
+        if n > 0 and colors.size != n * width * height * 3:
+            raise ValueError("colors must hold nViews * H * W * 3 bytes")
+        mean = np.zeros((P, 3), dtype=np.uint8)
+        median = np.zeros((P, 3), dtype=np.uint8)
+        nb = np.zeros((P,), dtype=np.int32)
+        self._ck(self._lib.dmi_colorize(self._h, P, _ptr(xyz), scalar_code(xyz.dtype), n, _ptr(colors), _ptr(K), _ptr(RT),
+                                        int(width), int(height), _ptr(mean), _ptr(median), _ptr(nb)))
+        return mean, median, nb
+
+    def colorize_device(self, n_points: int, d_xyz: int, xyz_dtype, n_views: int, d_colors: int, K, RT,
+                        width: int, height: int, d_mean: int, d_median: int, d_nb: int):
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        self._ck(self._lib.dmi_colorize_device(self._h, int(n_points), _ptr(int(d_xyz)), scalar_code(xyz_dtype), int(n_views),
+                                               _ptr(int(d_colors)), _ptr(K), _ptr(RT), int(width), int(height),
+                                               _ptr(int(d_mean)), _ptr(int(d_median)), _ptr(int(d_nb))))
+
+    def color_kernel_stats(self):
+        ms = C.c_float()
+        n = C.c_longlong()
+        self._ck(self._lib.dmi_color_kernel_stats(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    # -- measurement -----------------------------------------------------------------------------
+    def launch_counter(self) -> int:
+        n = C.c_longlong()
+        self._ck(self._lib.dmi_launch_counter(self._h, C.byref(n)))
+        return int(n.value)
+
+    def measure_fp_peak(self, which: int, ms_target: float = 200.0) -> float:
+        t = C.c_double()
+        self._ck(self._lib.dmi_measure_fp_peak(self._h, int(which), float(ms_target), C.byref(t)))
+        return float(t.value)

@@ -1,0 +1,165 @@
+/*
+ * dmi_b200.h -- C ABI of the B200-native depth-map integration engine.
+ *
+ * This is the drop-in boundary for the one hot path of bastienjacquet/CudaDepthMapIntegration:
+ * the two free functions the reference's filter forward-declares and calls
+ * (Reconstruction/vtkCudaReconstructionFilter.cxx:65-71, called at :171-176),
+ *
+ *     void CudaInitialize(vtkMatrix4x4*, int gridDims[3], double gridOrig[3], double gridSpacing[3],
+ *                         double thick, double rho, double eta, double delta, int depthMapDims[2]);
+ *     template <typename T> bool ProcessDepthMap(std::vector<std::string> vtiList,
+ *                         std::vector<std::string> krtdList, double thresholdBestCost,
+ *                         vtkDoubleArray* io_scalar);
+ *
+ * (defined in Reconstruction/CudaReconstruction.cu:269-298 and :302-386), plus the per-point loop of
+ * MeshColoration::ProcessColoration (Coloration/MeshColoration.cxx:98-199).  File reading (VTK XML,
+ * .krtd) stays on the caller's side of the boundary: every function takes plain pointers and sizes.
+ *
+ * Conventions shared by all entry points
+ *   - every function returns DMI_OK (0) or a DMI_ERR_* code; it never calls exit() (the reference
+ *     does, CudaReconstruction.cu:68-76).  dmi_last_error() gives the message.
+ *   - 4x4 matrices are 16 doubles, row-major (the order vtkMatrixToTypeComputeTable produces,
+ *     CudaReconstruction.cu:220-230).  K is the 3x3 intrinsics inside an identity 4x4
+ *     (Sources/ReconstructionData.cxx:199-209), RT = [R | t] with last row 0 0 0 1 (Sources/Helper.h:161-165).
+ *   - images are bottom-up (VTK), row r of storage = image row H-1-r (CudaReconstruction.cu:141-149).
+ *   - depth -1 means "no measurement" (CudaReconstruction.cu:202).
+ *   - the volume is the reference's cell array: (dims[0]-1)*(dims[1]-1)*(dims[2]-1) scalars, id =
+ *     (k*Ny + j)*Nx + i (CudaReconstruction.cu:126-134), where dims are vtkImageData POINT dims.
+ *   - one context = one GPU = one caller thread.  Calls taking HOST pointers are synchronous; calls
+ *     taking DEVICE pointers are asynchronous on the context's stream (see dmi_set_stream).
+ *   - there is no CPU fallback anywhere behind this header.
+ */
+#ifndef DMI_B200_H
+#define DMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMI_ABI_VERSION 1
+
+/* status codes */
+#define DMI_OK 0
+#define DMI_ERR_INVALID_ARGUMENT 1   /* null pointer, bad size, bad enum */
+#define DMI_ERR_NOT_INITIALIZED 2    /* dmi_initialize / volume_begin not called yet */
+#define DMI_ERR_CUDA 3               /* a CUDA runtime call failed; message has the CUDA error */
+#define DMI_ERR_NO_VIEWS 4           /* nViews == 0 (CudaReconstruction.cu:308-312 returns false) */
+#define DMI_ERR_BAD_PARAMETERS 5     /* Rho == 0 && Thick == 0 (vtkCudaReconstructionFilter.cxx:138-142) */
+#define DMI_ERR_OUT_OF_MEMORY 6
+
+/* scalar types: TVolumetric of ProcessDepthMap<T> (CudaReconstruction.cu:390-400); mesh point storage */
+#define DMI_F32 0
+#define DMI_F64 1
+
+/* integration kernel selection (dmi_set_option DMI_OPT_TSDF_KERNEL) */
+#define DMI_TSDF_KERNEL_AUTO 0       /* certified fast path with exact fallback */
+#define DMI_TSDF_KERNEL_EXACT 1      /* every voxel*view through the reference's exact op sequence */
+
+#define DMI_OPT_TSDF_KERNEL 1
+#define DMI_OPT_VIEW_CHUNK 2         /* views per launch (0 = auto) */
+
+typedef struct dmi_ctx dmi_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+int dmi_abi_version(void);
+int dmi_device_count(int* count);
+/* Creates a context bound to CUDA device `device`.  On failure *ctx is NULL and
+ * dmi_last_error(NULL) holds the reason (thread-local). */
+int dmi_create(int device, dmi_ctx** ctx);
+int dmi_destroy(dmi_ctx* ctx);
+const char* dmi_last_error(const dmi_ctx* ctx);
+/* Run the context's work on an existing CUDA stream (a cudaStream_t passed as void*), e.g. the
+ * caller's framework stream; NULL restores the context's own stream. */
+int dmi_set_stream(dmi_ctx* ctx, void* cuda_stream);
+int dmi_synchronize(dmi_ctx* ctx);
+int dmi_set_option(dmi_ctx* ctx, int option, long long value);
+
+/* ---- TSDF integration ---------------------------------------------------------------------- */
+
+/* Replaces CudaInitialize (CudaReconstruction.cu:269-298): same arguments, same meaning, with the
+ * vtkMatrix4x4 flattened to 16 row-major doubles.  gridDims are POINT dims.  State lives in the
+ * context, not in process-global __constant__ symbols, so contexts are independent. */
+int dmi_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims[3],
+                   const double gridOrig[3], const double gridSpacing[3],
+                   double rayPotentialThick, double rayPotentialRho, double rayPotentialEta,
+                   double rayPotentialDelta, const int depthMapDims[2]);
+
+/* z-slab sharding (new; the reference is single-GPU): this context owns cells k in [k0, k1) of the
+ * grid given to dmi_initialize.  Voxel centres keep their GLOBAL index arithmetic
+ * (orig + (k + 0.5) * spacing, CudaReconstruction.cu:78-83), so slabs concatenate bit-identically.
+ * Default after dmi_initialize: the whole grid.  Volume pointers below then cover the slab only. */
+int dmi_set_slab(dmi_ctx* ctx, int k0, int k1);
+
+/* Replaces ProcessDepthMap<T> (CudaReconstruction.cu:302-386) for views already in host memory:
+ * uploads io_scalar (the call ACCUMULATES onto its content, :323-327), applies the best-cost
+ * threshold filter of ReconstructionData::ApplyDepthThresholdFilter (depth := -1 where
+ * bestCost > threshold; skipped when bestCost is NULL), integrates the views in list order, and
+ * writes the result back into io_scalar.
+ *   depths, bestCost  double[nViews][H][W]      K, RT  double[nViews][16]
+ *   io_scalar         slab cells of type scalarType (DMI_F32 / DMI_F64)                        */
+int dmi_process_depth_maps(dmi_ctx* ctx, int nViews, const double* depths, const double* bestCost,
+                           double thresholdBestCost, const double* K, const double* RT,
+                           void* io_scalar, int scalarType);
+
+/* Streaming form of the same thing, for callers that read files view by view like the reference's
+ * loop (:343-365) or keep data on the GPU:
+ *   begin      allocates the slab on the device; uploads h_scalar, or zero-fills when NULL
+ *   integrate  adds nViews views (host or device pointers; K/RT are always host pointers)
+ *   end        downloads the slab into h_scalar (may be NULL to keep it on the device)          */
+int dmi_volume_begin(dmi_ctx* ctx, const void* h_scalar, int scalarType);
+int dmi_volume_integrate_host(dmi_ctx* ctx, int nViews, const double* depths, const double* bestCost,
+                              double thresholdBestCost, const double* K, const double* RT);
+int dmi_volume_integrate_device(dmi_ctx* ctx, int nViews, const double* d_depths,
+                                const double* d_bestCost, double thresholdBestCost,
+                                const double* K, const double* RT);
+int dmi_volume_end(dmi_ctx* ctx, void* h_scalar);
+/* Device address and size in bytes of the slab (valid between begin and the next begin/destroy). */
+int dmi_volume_device_ptr(dmi_ctx* ctx, void** d_ptr, size_t* bytes);
+
+/* ReconstructionData::ApplyDepthThresholdFilter (Sources/ReconstructionData.cxx:138-167) on device
+ * buffers, in place: d_depths[i] = -1 where d_bestCost[i] > threshold. */
+int dmi_apply_depth_threshold_device(dmi_ctx* ctx, size_t count, double* d_depths,
+                                     const double* d_bestCost, double thresholdBestCost);
+
+/* Device time (ms, CUDA events on the context's stream) and launch count of the integration kernels
+ * issued since the last call to this function. */
+int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
+
+/* ---- mesh coloration ----------------------------------------------------------------------- */
+
+/* Replaces the loop of MeshColoration::ProcessColoration (Coloration/MeshColoration.cxx:140-192)
+ * together with ReconstructionData::TransformWorldToDepthMapPosition / GetColorValue
+ * (Sources/ReconstructionData.cxx:169-182, 92-116) and help::ComputeMedian (Sources/Helper.h:174-187).
+ *   xyz       nPoints * 3 coordinates, DMI_F32 (vtkPoints' default storage) or DMI_F64
+ *   colors    uint8[nViews][H][W][3] bottom-up ("Color" arrays); W, H = view 0's dims (:110)
+ *   mean      uint8[nPoints][3]  "MeanColoration"     (integer sum / count, truncated)
+ *   median    uint8[nPoints][3]  "MedianColoration"   (even count: (a+b)/2 truncated)
+ *   nbProjected int32[nPoints]   "NbProjectedDepthMap"
+ * Points no view sees get 0/0/0 and count 0 (:116-118,124-126,132).                             */
+int dmi_colorize(dmi_ctx* ctx, size_t nPoints, const void* xyz, int xyzType, int nViews,
+                 const uint8_t* colors, const double* K, const double* RT, int W, int H,
+                 uint8_t* mean, uint8_t* median, int32_t* nbProjected);
+/* Same with every array except K/RT already on the device (asynchronous on the context stream). */
+int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyzType, int nViews,
+                        const uint8_t* d_colors, const double* K, const double* RT, int W, int H,
+                        uint8_t* d_mean, uint8_t* d_median, int32_t* d_nbProjected);
+int dmi_color_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
+
+/* ---- measurement helpers ------------------------------------------------------------------- */
+
+/* Number of kernels this library has launched on behalf of the context since dmi_create. */
+int dmi_launch_counter(dmi_ctx* ctx, long long* launches);
+
+/* Issue-rate microbenchmarks used for the roofline denominators that MEASURED_PEAKS.json lacks.
+ * which: 0 = FP64 DFMA, 1 = FP32 FFMA.  Returns sustained TFLOP/s (FMA = 2 flops) over `ms_target`
+ * milliseconds of back-to-back launches. */
+int dmi_measure_fp_peak(dmi_ctx* ctx, int which, double ms_target, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMI_B200_H */

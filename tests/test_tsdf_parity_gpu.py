@@ -1,0 +1,245 @@
+"""GPU parity of the integration path, through the C ABI, against the oracle (and, where built, the
+reference's own kernel recompiled for sm_100a).
+
+Bars (BASELINE.json north_star): every discrete decision (pixel, validity, branch) identical; voxel
+values within 1e-5 relative / 1e-6 absolute.  The exact kernel is held to BIT equality with the
+oracle / the -fmad=false reference build."""
+import numpy as np
+import pytest
+
+from cudadepthmapintegration_b200 import _lib
+from tests import _oracle
+from tests.scenes import Scene
+from tests.test_oracle_pinning import CASES, make_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6      # north_star tolerance for TSDF voxel values
+
+
+def run_gpu(ctx, s, dtype, best_cost=True, threshold=0.14, start=None, kernel=_lib.DMI_TSDF_KERNEL_AUTO, slab=None):
+    ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, kernel)
+    ctx.initialize(s.grid.matrix, s.grid.point_dims, s.grid.origin, s.grid.spacing,
+                   s.rp.thick, s.rp.rho, s.rp.eta, s.rp.delta, (s.W, s.H))
+    if slab is not None:
+        ctx.set_slab(*slab)
+    n = ctx.slab_cells
+    out = np.zeros(n, dtype=dtype) if start is None else start.astype(dtype).copy()
+    ctx.process_depth_maps(s.depths, s.best_cost if best_cost else None, threshold, s.K, s.RT, out)
+    return out
+
+
+def assert_close(got, want):
+    got = got.astype(np.float64); want = want.astype(np.float64)
+    err = np.abs(got - want)
+    ok = err <= ATOL + RTOL * np.abs(want)
+    assert ok.all(), f"{(~ok).sum()} voxels out of tolerance, max abs err {err.max():.3e}"
+
+
+@pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_small_cases_against_oracle(gpu_ctx, oracle, name, kernel):
+    s, dtype = make_case(name)
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros(dtype))
+    got = run_gpu(gpu_ctx, s, dtype, kernel=kernel)
+    assert np.count_nonzero(want) > 0
+    if kernel == _lib.DMI_TSDF_KERNEL_EXACT:
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    else:
+        # identical decisions => identical set of touched voxels; values within tolerance
+        assert np.array_equal(got != 0, want != 0)
+        assert_close(got, want)
+
+
+@pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
+def test_config2_128cube_10_views_640x480(gpu_ctx, oracle, kernel):
+    # BASELINE.json configs[1]
+    s = Scene(128, 10, 640, 480, depth_noise=0.25)
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    got = run_gpu(gpu_ctx, s, np.float64, kernel=kernel)
+    if kernel == _lib.DMI_TSDF_KERNEL_EXACT:
+        assert np.array_equal(got, want)
+    else:
+        assert np.array_equal(got != 0, want != 0)
+        assert_close(got, want)
+
+
+def test_against_reference_kernel_recompiled(gpu_ctx, oracle):
+    ref_nofma = _oracle.load_ref_cuda(nofma=True)
+    ref_o3 = _oracle.load_ref_cuda(nofma=False)
+    if ref_nofma is None or ref_o3 is None:
+        pytest.skip("oracle/_ref CUDA builds not present")
+    s = Scene(96, 8, 320, 240, rotate_deg=30.0, depth_noise=0.25)
+    filtered = oracle.apply_depth_threshold(s.depths, s.best_cost, 0.14)
+    want_nofma, _, _ = ref_nofma.run(s.grid, s.rp, s.W, s.H, filtered, s.K, s.RT, s.zeros())
+    want_o3, _, _ = ref_o3.run(s.grid, s.rp, s.W, s.H, filtered, s.K, s.RT, s.zeros())
+    orc = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    # the oracle IS the reference kernel without FMA contraction (the shipped -G build), bit for bit
+    assert np.array_equal(orc, want_nofma)
+    got_exact = run_gpu(gpu_ctx, s, np.float64, kernel=_lib.DMI_TSDF_KERNEL_EXACT)
+    assert np.array_equal(got_exact, want_nofma)
+    got = run_gpu(gpu_ctx, s, np.float64)
+    assert_close(got, want_nofma)
+    assert_close(got, want_o3)
+
+
+@pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
+def test_accumulates_onto_io_scalar_and_view_order(gpu_ctx, oracle, kernel):
+    s = Scene(40, 6, 96, 72)
+    start = np.linspace(-2, 2, s.grid.n_voxels)
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, None, 0.0, s.K, s.RT, start.copy())
+    got = run_gpu(gpu_ctx, s, np.float64, best_cost=False, start=start, kernel=kernel)
+    if kernel == _lib.DMI_TSDF_KERNEL_EXACT:
+        assert np.array_equal(got, want)
+    else:
+        assert_close(got, want)
+    # two calls of 3 views == one call of 6 views, bit for bit (same accumulation order per voxel)
+    ctx = gpu_ctx
+    ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, kernel)
+    ctx.initialize(s.grid.matrix, s.grid.point_dims, s.grid.origin, s.grid.spacing,
+                   s.rp.thick, s.rp.rho, s.rp.eta, s.rp.delta, (s.W, s.H))
+    two = start.copy()
+    ctx.process_depth_maps(s.depths[:3], None, 0.0, s.K[:3], s.RT[:3], two)
+    ctx.process_depth_maps(s.depths[3:], None, 0.0, s.K[3:], s.RT[3:], two)
+    assert np.array_equal(two, got)
+
+
+@pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
+def test_z_slabs_concatenate_bit_identically(gpu_ctx, kernel):
+    s = Scene((37, 21, 19), 5, 80, 60, rotate_deg=30.0)
+    whole = run_gpu(gpu_ctx, s, np.float64, kernel=kernel)
+    nz = s.grid.n_cells[2]
+    parts = [run_gpu(gpu_ctx, s, np.float64, kernel=kernel, slab=r) for r in [(0, 5), (5, 6), (6, 6), (6, nz)]]
+    assert np.array_equal(np.concatenate(parts), whole)
+
+
+@pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
+def test_view_chunking_does_not_change_results(gpu_ctx, kernel):
+    s = Scene(24, 70, 48, 36)          # more views than one launch chunk
+    a = run_gpu(gpu_ctx, s, np.float64, kernel=kernel)
+    gpu_ctx.set_option(_lib.DMI_OPT_VIEW_CHUNK, 7)
+    try:
+        b = run_gpu(gpu_ctx, s, np.float64, kernel=kernel)
+    finally:
+        gpu_ctx.set_option(_lib.DMI_OPT_VIEW_CHUNK, 0)
+    assert np.array_equal(a, b)
+
+
+def edge_scene():
+    """Voxel exactly at the camera centre (0/0 -> NaN pixel), h.z == 0 (+-inf pixel), voxels behind the
+    camera, projections exactly on x.5, depth == -1, an all-invalid view.  Everything is exact in binary."""
+    from cudadepthmapintegration_b200 import synthetic as syn
+    W, H = 16, 12
+    grid = syn.Grid((8, 8, 8), np.array([-4.0, -4.0, -4.0]), np.array([1.0, 1.0, 1.0]), np.eye(4).reshape(16))
+    rp = syn.RayPotential(thick=0.5, rho=0.75, eta=0.25, delta=2.0)
+    K = np.eye(4); K[0, 0] = K[1, 1] = 4.0; K[0, 2] = 8.0; K[1, 2] = 6.0
+    views_K, views_RT = [], []
+    # camera centres exactly on voxel centres, axis-aligned
+    for c in ([0.5, 0.5, 0.5], [0.5, 0.5, -3.5], [-1.5, 2.5, -0.5]):
+        RT = np.eye(4); RT[:3, 3] = -np.array(c)
+        views_K.append(K.reshape(16)); views_RT.append(RT.reshape(16))
+    Ks = np.array(views_K); RTs = np.array(views_RT)
+    rng = np.random.RandomState(5)
+    depths = rng.uniform(0.5, 6.0, size=(3, H, W))
+    depths[rng.uniform(size=depths.shape) < 0.3] = -1.0
+    depths[2] = -1.0                                  # a view with no valid pixel at all
+    depths[0, H - 1, 0] = 1.25                        # pixel (0,0): would be hit if NaN converted to 0
+    return grid, rp, W, H, depths, Ks, RTs
+
+
+@pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
+def test_edge_cases_match_oracle(gpu_ctx, oracle, kernel):
+    grid, rp, W, H, depths, Ks, RTs = edge_scene()
+    want = oracle.tsdf_integrate(grid, rp, W, H, depths, None, 0.0, Ks, RTs, np.zeros(512))
+    gpu_ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, kernel)
+    gpu_ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
+    got = np.zeros(512)
+    gpu_ctx.process_depth_maps(depths, None, 0.0, Ks, RTs, got)
+    assert np.count_nonzero(want) > 100
+    assert np.array_equal(got, want)
+
+
+def test_edge_cases_reference_kernel(oracle):
+    """Pins the oracle's device-conversion semantics (NaN, +-inf, saturation) on the reference's own
+    kernel running on this GPU: both nvcc builds must agree with the oracle bit for bit."""
+    grid, rp, W, H, depths, Ks, RTs = edge_scene()
+    want = oracle.tsdf_integrate(grid, rp, W, H, depths, None, 0.0, Ks, RTs, np.zeros(512))
+    for nofma in (True, False):
+        ref = _oracle.load_ref_cuda(nofma=nofma)
+        if ref is None:
+            pytest.skip("oracle/_ref CUDA builds not present")
+        got, _, _ = ref.run(grid, rp, W, H, depths, Ks, RTs, np.zeros(512))
+        assert np.array_equal(got, want)
+
+
+def test_threshold_filter_on_device(gpu_ctx, oracle):
+    import torch
+    rng = np.random.RandomState(1)
+    d = rng.uniform(1, 3, size=10007); c = rng.uniform(0, 0.2, size=10007)
+    want = oracle.apply_depth_threshold(d, c, 0.14)
+    td = torch.from_numpy(d).cuda(); tc = torch.from_numpy(c).cuda()
+    gpu_ctx.apply_depth_threshold_device(d.size, td.data_ptr(), tc.data_ptr(), 0.14)
+    gpu_ctx.synchronize()
+    assert np.array_equal(td.cpu().numpy(), want)
+    # misaligned (8-byte offset) view
+    td = torch.from_numpy(d).cuda(); tc = torch.from_numpy(c).cuda()
+    gpu_ctx.apply_depth_threshold_device(d.size - 1, td.data_ptr() + 8, tc.data_ptr() + 8, 0.14)
+    gpu_ctx.synchronize()
+    assert np.array_equal(td.cpu().numpy()[1:], want[1:])
+
+
+def test_device_resident_views_and_const_inputs(gpu_ctx, oracle):
+    import torch
+    s = Scene(32, 5, 64, 48)
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    ctx = gpu_ctx
+    ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_EXACT)
+    ctx.initialize(s.grid.matrix, s.grid.point_dims, s.grid.origin, s.grid.spacing,
+                   s.rp.thick, s.rp.rho, s.rp.eta, s.rp.delta, (s.W, s.H))
+    td = torch.from_numpy(s.depths).cuda(); tb = torch.from_numpy(s.best_cost).cuda()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        ctx.volume_begin(None, np.float64)
+        ctx.volume_integrate_device(s.n_views, td.data_ptr(), tb.data_ptr(), 0.14, s.K, s.RT)
+        out = np.empty(s.grid.n_voxels)
+        ctx.volume_end(out)
+    finally:
+        ctx.set_stream(None)
+    assert np.array_equal(out, want)
+    assert np.array_equal(td.cpu().numpy(), s.depths)       # the caller's depth maps are not modified
+    ms, launches = ctx.tsdf_kernel_stats()
+    assert launches >= 1 and ms > 0
+
+
+def test_error_codes(gpu_ctx):
+    from cudadepthmapintegration_b200 import DmiError
+    s = Scene(8, 2, 16, 12)
+    with pytest.raises(DmiError) as e:
+        gpu_ctx.initialize(s.grid.matrix, s.grid.point_dims, s.grid.origin, s.grid.spacing, 0.0, 0.0, 0.1, 0.3, (16, 12))
+    assert e.value.code == _lib.DMI_ERR_BAD_PARAMETERS          # vtkCudaReconstructionFilter.cxx:138-142
+    gpu_ctx.initialize(s.grid.matrix, s.grid.point_dims, s.grid.origin, s.grid.spacing, 0.1, 0.8, 0.1, 0.3, (16, 12))
+    with pytest.raises(DmiError) as e:
+        gpu_ctx.process_depth_maps(np.zeros((0, 12, 16)), None, 0.0, np.zeros((0, 16)), np.zeros((0, 16)), np.zeros(512))
+    assert e.value.code == _lib.DMI_ERR_NO_VIEWS                # CudaReconstruction.cu:308-312
+    with pytest.raises(DmiError):
+        gpu_ctx.set_slab(3, 2)
+
+
+def test_filter_class_mirrors_reference_api(oracle):
+    from cudadepthmapintegration_b200 import CudaReconstructionFilter
+    s = Scene(20, 4, 48, 36)
+    f = CudaReconstructionFilter()
+    f.SetInputGrid(s.grid.point_dims, s.grid.origin, s.grid.spacing)
+    f.SetGridMatrix(s.grid.matrix)
+    f.SetViews(s.depths, s.best_cost, s.K, s.RT)
+    assert f.Update() == 0                                      # Rho == Thick == 0 -> error path, returns 0
+    f.SetRayPotentialThickness(s.rp.thick); f.SetRayPotentialRho(s.rp.rho)
+    f.SetRayPotentialEta(s.rp.eta); f.SetRayPotentialDelta(s.rp.delta)
+    f.SetThresholdBestCost(0.14)
+    assert f.Update() == 1
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    got = f.GetOutput()
+    assert got.shape == (20, 20, 20)
+    assert_close(got.reshape(-1), want)
+    assert f.GetExecutionTime() > 0
+    f.close()
