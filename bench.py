@@ -249,7 +249,15 @@ def main():
     torch.cuda.synchronize()
 
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    gathered = torch.empty((N - 0, ), dtype=torch.float64, device=dev)[:0]  # placeholder
+    full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
+
+    def _as_tensor(ptr, count):
+        """Wrap the context's slab (device memory owned by libdmi_b200) as a tensor, without copying."""
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        return torch.as_tensor(h, device=dev)
 
     def step_device():
         """One full job with inputs resident in HBM."""
@@ -287,24 +295,18 @@ def main():
             ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
         # the finished slabs are gathered once (for contouring on rank 0)
         ptr, nbytes = ctx.volume_device_ptr()
-        slab = torch.empty(0)
-        # wrap the slab without copying
-        slab = _as_tensor(ptr, (k1 - k0) * N * N, dev)
+        slab = _as_tensor(ptr, (k1 - k0) * N * N)
+        # slabs may differ by one plane: gather with explicit point-to-point transfers
         if rank == 0:
-            outs = [full_volume[sharding.slab_range(N, r, world)[0] * N * N: sharding.slab_range(N, r, world)[1] * N * N] for r in range(world)]
-            dist.gather(slab, outs, dst=0)
+            full_volume[k0 * N * N:k1 * N * N].copy_(slab)
+            reqs = []
+            for r in range(1, world):
+                a, b = sharding.slab_range(N, r, world)
+                reqs.append(dist.irecv(full_volume[a * N * N:b * N * N], src=r))
+            for q in reqs:
+                q.wait()
         else:
-            dist.gather(slab, None, dst=0)
-
-    def _as_tensor(ptr, count, device):
-        import ctypes
-        class _Holder:
-            pass
-        h = _Holder()
-        h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-        return torch.as_tensor(h, device=device)
-
-    full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
+            dist.send(slab, dst=0)
 
     def barrier():
         if world > 1:

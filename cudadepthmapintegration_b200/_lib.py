@@ -24,6 +24,8 @@ DMI_TSDF_KERNEL_AUTO = 0
 DMI_TSDF_KERNEL_EXACT = 1
 DMI_OPT_TSDF_KERNEL = 1
 DMI_OPT_VIEW_CHUNK = 2
+DMI_OPT_TIER_COUNTERS = 3
+DMI_OPT_CULL = 4
 
 
 class DmiError(RuntimeError):
@@ -46,6 +48,7 @@ _PROTOTYPES = {
     "dmi_destroy": (C.c_int, [_vp]),
     "dmi_last_error": (C.c_char_p, [_vp]),
     "dmi_set_stream": (C.c_int, [_vp, _vp]),
+    "dmi_use_own_stream": (C.c_int, [_vp]),
     "dmi_synchronize": (C.c_int, [_vp]),
     "dmi_set_option": (C.c_int, [_vp, _i, _ll]),
     "dmi_initialize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp]),
@@ -58,6 +61,7 @@ _PROTOTYPES = {
     "dmi_volume_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "dmi_apply_depth_threshold_device": (C.c_int, [_vp, _sz, _vp, _vp, _d]),
     "dmi_tsdf_kernel_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_ll)]),
+    "dmi_tsdf_tier_counters": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "dmi_colorize": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dmi_colorize_device": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dmi_color_kernel_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_ll)]),

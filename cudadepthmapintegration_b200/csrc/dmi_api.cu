@@ -78,6 +78,10 @@ struct dmi_ctx
   KernelStats tsdf_stats, color_stats;
   long long opt_kernel = DMI_TSDF_KERNEL_AUTO, opt_chunk = 0;
   long long total_launches = 0;
+  dmi::FastChunk fast_chunk{};
+  DevBuf counters, cls, tiles;
+  bool counters_on = false;
+  bool opt_cull = true;
   std::string err;
 
   int fail(int code, const std::string& msg) { err = msg; return code; }
@@ -160,6 +164,8 @@ int dmi_destroy(dmi_ctx* ctx)
     if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
   }
   ctx->filtered.release();
+  ctx->counters.release();
+  ctx->cls.release(); ctx->tiles.release();
   ctx->c_xyz.release(); ctx->c_colors.release(); ctx->c_mats.release();
   ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release();
   ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
@@ -177,7 +183,14 @@ const char* dmi_last_error(const dmi_ctx* ctx)
 int dmi_set_stream(dmi_ctx* ctx, void* cuda_stream)
 {
   if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
-  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return DMI_OK;
+}
+
+int dmi_use_own_stream(dmi_ctx* ctx)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  ctx->stream = ctx->own_stream;
   return DMI_OK;
 }
 
@@ -198,6 +211,17 @@ int dmi_set_option(dmi_ctx* ctx, int option, long long value)
     case DMI_OPT_TSDF_KERNEL:
       DMI_REQUIRE(value == DMI_TSDF_KERNEL_AUTO || value == DMI_TSDF_KERNEL_EXACT, "unknown TSDF kernel id");
       ctx->opt_kernel = value; return DMI_OK;
+    case DMI_OPT_CULL:
+      ctx->opt_cull = value != 0; return DMI_OK;
+    case DMI_OPT_TIER_COUNTERS:
+      ctx->counters_on = value != 0;
+      if (ctx->counters_on)
+      {
+        DMI_CK(cudaSetDevice(ctx->device));
+        DMI_CK(ctx->counters.ensure(sizeof(dmi::FastCounters)));
+        DMI_CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(dmi::FastCounters), ctx->stream));
+      }
+      return DMI_OK;
     case DMI_OPT_VIEW_CHUNK:
       DMI_REQUIRE(value >= 0, "view chunk must be >= 0");
       ctx->opt_chunk = value; return DMI_OK;
@@ -267,14 +291,22 @@ int dmi_volume_begin(dmi_ctx* ctx, const void* h_scalar, int scalarType)
   return DMI_OK;
 }
 
-// Launches the integration kernels for nViews views whose (already filtered) depth maps sit at d_depths.
-static int integrate_resident(dmi_ctx* ctx, int nViews, const double* d_depths, const double* K, const double* RT)
+static bool fast_path_applies(const dmi_ctx* ctx)
+{
+  // The certified fast path needs the regime the reference's CLI enforces (0 < Thick, finite
+  // parameters; Reconstruction/main.cxx:270-271) and pixel / voxel coordinates that floats hold
+  // exactly; anything else goes through the exact kernel.
+  const dmi::GridParams& g = ctx->g;
+  return ctx->opt_kernel == DMI_TSDF_KERNEL_AUTO && g.thick > 0 && std::isfinite(g.rho_over_thick) &&
+         std::isfinite(g.delta) && std::isfinite(g.neg_eta_rho) && std::isfinite(g.rho) && g.W < (1 << 21) &&
+         g.H < (1 << 21) && g.Nx < (1 << 23) && g.Ny < (1 << 23) && g.Nz < (1 << 23);
+}
+
+// Exact kernel over views whose depth maps at d_depths are ALREADY filtered.
+static int integrate_exact_resident(dmi_ctx* ctx, int nViews, const double* d_depths, const double* K, const double* RT)
 {
   const dmi::GridParams& g = ctx->g;
-  if (slab_cells(g) == 0) return DMI_OK;
   const size_t npix = (size_t)g.W * g.H;
-  EventSpan span = ctx->tsdf_stats.open();
-  DMI_CK(cudaEventRecord(span.a, ctx->stream));
   int chunk = dmi::kExactChunk;
   if (ctx->opt_chunk > 0 && ctx->opt_chunk < chunk) chunk = (int)ctx->opt_chunk;
   for (int v0 = 0; v0 < nViews; v0 += chunk)
@@ -291,6 +323,93 @@ static int integrate_resident(dmi_ctx* ctx, int nViews, const double* d_depths, 
     ctx->tsdf_stats.launches++;
     ctx->total_launches++;
   }
+  return DMI_OK;
+}
+
+// Fast kernel over views given as the caller's depth maps + optional best-cost maps (neither modified):
+// the filter is folded into the float classification image built by the view-preparation kernel.
+static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_cost, double thr,
+                                   const double* K, const double* RT)
+{
+  const dmi::GridParams& g = ctx->g;
+  const size_t npix = (size_t)g.W * g.H;
+  const size_t tilesPerView = (size_t)((g.W + 15) / 16) * ((g.H + 15) / 16);
+  int chunk = dmi::kFastChunk;
+  if (ctx->opt_chunk > 0 && ctx->opt_chunk < chunk) chunk = (int)ctx->opt_chunk;
+  // views prepared at a time: whole chunks, about 1 GB of classification image
+  int group = (int)std::max<size_t>(1, (1ull << 30) / (npix * 4));
+  group = std::max(chunk, group / chunk * chunk);
+  group = std::min(group, (nViews + chunk - 1) / chunk * chunk);
+  DMI_CK(ctx->cls.ensure((size_t)group * npix * 4));
+  DMI_CK(ctx->tiles.ensure((size_t)group * tilesPerView * 4));
+  dmi::FastChunk* c = &ctx->fast_chunk;
+  dmi::fill_fast_chunk_constants(g, c);
+  for (int g0 = 0; g0 < nViews; g0 += group)
+  {
+    const int gn = std::min(group, nViews - g0);
+    DMI_CK(dmi::launch_prepare_views(d_depths + npix * g0, d_cost ? d_cost + npix * g0 : nullptr, thr, gn, g.W, g.H,
+                                     (float*)ctx->cls.p, (float*)ctx->tiles.p, ctx->stream));
+    ctx->total_launches++;
+    for (int v0 = 0; v0 < gn; v0 += chunk)
+    {
+      c->n = std::min(chunk, gn - v0);
+      c->pinhole = 1;
+      for (int q = 0; q < c->n; q++)
+      {
+        const double* k16 = K + 16 * (size_t)(g0 + v0 + q);
+        const double* rt16 = RT + 16 * (size_t)(g0 + v0 + q);
+        dmi::compose_fast_view(g, k16, rt16, c->cxc, c->cyc, &c->v[q]);
+        memcpy(c->e[q].RT, rt16, sizeof(double) * 12);
+        memcpy(c->e[q].K, k16, sizeof(double) * 12);
+        if (!(k16[8] == 0.0 && k16[9] == 0.0 && k16[10] == 1.0 && k16[11] == 0.0)) c->pinhole = 0;
+      }
+      DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths + npix * (g0 + v0), (const float*)ctx->cls.p + npix * v0,
+                                   (const float*)ctx->tiles.p + tilesPerView * v0, ctx->opt_cull, ctx->vol.p,
+                                   ctx->vol_type, ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr,
+                                   ctx->stream));
+      ctx->tsdf_stats.launches++;
+      ctx->total_launches++;
+    }
+  }
+  return DMI_OK;
+}
+
+// Integrates nViews views resident on the device.  d_cost may be null.  When `scratch_ok` the depth
+// buffer belongs to the library (a staging slot) and may be filtered in place.
+static int integrate_device_views(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_cost, double thr,
+                                  const double* K, const double* RT, bool scratch_ok)
+{
+  const dmi::GridParams& g = ctx->g;
+  if (slab_cells(g) == 0) return DMI_OK;
+  const size_t npix = (size_t)g.W * g.H;
+  EventSpan span = ctx->tsdf_stats.open();
+  DMI_CK(cudaEventRecord(span.a, ctx->stream));
+  int rc = DMI_OK;
+  if (fast_path_applies(ctx))
+    rc = integrate_fast_resident(ctx, nViews, d_depths, d_cost, thr, K, RT);
+  else if (!d_cost)
+    rc = integrate_exact_resident(ctx, nViews, d_depths, K, RT);
+  else if (scratch_ok)
+  {
+    DMI_CK(dmi::launch_depth_threshold(const_cast<double*>(d_depths), d_cost, (size_t)nViews * npix, thr, ctx->stream));
+    ctx->total_launches++;
+    rc = integrate_exact_resident(ctx, nViews, d_depths, K, RT);
+  }
+  else
+  {
+    // the caller's depth buffer is const: filter into scratch, a bounded number of views at a time
+    const int step = (int)std::max<size_t>(1, std::min<size_t>((size_t)nViews, (512ull << 20) / (npix * 8)));
+    DMI_CK(ctx->filtered.ensure((size_t)step * npix * 8));
+    for (int v0 = 0; v0 < nViews && rc == DMI_OK; v0 += step)
+    {
+      const int n = std::min(step, nViews - v0);
+      DMI_CK(cudaMemcpyAsync(ctx->filtered.p, d_depths + npix * v0, (size_t)n * npix * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      DMI_CK(dmi::launch_depth_threshold((double*)ctx->filtered.p, d_cost + npix * v0, (size_t)n * npix, thr, ctx->stream));
+      ctx->total_launches++;
+      rc = integrate_exact_resident(ctx, n, (const double*)ctx->filtered.p, K + 16 * (size_t)v0, RT + 16 * (size_t)v0);
+    }
+  }
+  if (rc != DMI_OK) return rc;
   DMI_CK(cudaEventRecord(span.b, ctx->stream));
   ctx->tsdf_stats.pending.push_back(span);
   return DMI_OK;
@@ -304,21 +423,7 @@ int dmi_volume_integrate_device(dmi_ctx* ctx, int nViews, const double* d_depths
   if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
   DMI_REQUIRE(d_depths && K && RT, "null argument");
   DMI_CK(cudaSetDevice(ctx->device));
-  const size_t npix = (size_t)ctx->g.W * ctx->g.H;
-  if (!d_bestCost) return integrate_resident(ctx, nViews, d_depths, K, RT);
-  // The caller's depth buffer is const: filter into scratch, a bounded number of views at a time.
-  const int step = (int)std::max<size_t>(1, std::min<size_t>((size_t)nViews, (512ull << 20) / (npix * 8)));
-  DMI_CK(ctx->filtered.ensure((size_t)step * npix * 8));
-  for (int v0 = 0; v0 < nViews; v0 += step)
-  {
-    const int n = std::min(step, nViews - v0);
-    DMI_CK(cudaMemcpyAsync(ctx->filtered.p, d_depths + npix * v0, (size_t)n * npix * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    DMI_CK(dmi::launch_depth_threshold((double*)ctx->filtered.p, d_bestCost + npix * v0, (size_t)n * npix, thresholdBestCost, ctx->stream));
-    ctx->total_launches++;
-    int rc = integrate_resident(ctx, n, (const double*)ctx->filtered.p, K + 16 * (size_t)v0, RT + 16 * (size_t)v0);
-    if (rc != DMI_OK) return rc;
-  }
-  return DMI_OK;
+  return integrate_device_views(ctx, nViews, d_depths, d_bestCost, thresholdBestCost, K, RT, false);
 }
 
 int dmi_volume_integrate_host(dmi_ctx* ctx, int nViews, const double* depths, const double* bestCost,
@@ -346,13 +451,9 @@ int dmi_volume_integrate_host(dmi_ctx* ctx, int nViews, const double* depths, co
       DMI_CK(cudaMemcpyAsync(ctx->stage_cost[slot].p, bestCost + npix * v0, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     DMI_CK(cudaEventRecord(ctx->ev_ready[slot], ctx->copy_stream));
     DMI_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[slot], 0));
-    if (bestCost)
-    {
-      DMI_CK(dmi::launch_depth_threshold((double*)ctx->stage_depth[slot].p, (const double*)ctx->stage_cost[slot].p,
-                                         (size_t)n * npix, thresholdBestCost, ctx->stream));
-      ctx->total_launches++;
-    }
-    int rc = integrate_resident(ctx, n, (const double*)ctx->stage_depth[slot].p, K + 16 * (size_t)v0, RT + 16 * (size_t)v0);
+    int rc = integrate_device_views(ctx, n, (const double*)ctx->stage_depth[slot].p,
+                                    bestCost ? (const double*)ctx->stage_cost[slot].p : nullptr, thresholdBestCost,
+                                    K + 16 * (size_t)v0, RT + 16 * (size_t)v0, true);
     if (rc != DMI_OK) return rc;
     DMI_CK(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
     ctx->slot_used[slot] = true;
@@ -416,6 +517,17 @@ int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches)
   if (ms) *ms = ctx->tsdf_stats.drain(); else ctx->tsdf_stats.drain();
   if (launches) *launches = ctx->tsdf_stats.launches;
   ctx->tsdf_stats.launches = 0;
+  return DMI_OK;
+}
+
+int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[8])
+{
+  if (!ctx || !out) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->counters_on) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "enable DMI_OPT_TIER_COUNTERS first");
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(cudaStreamSynchronize(ctx->stream));
+  DMI_CK(cudaMemcpy(out, ctx->counters.p, sizeof(dmi::FastCounters), cudaMemcpyDeviceToHost));
+  DMI_CK(cudaMemset(ctx->counters.p, 0, sizeof(dmi::FastCounters)));
   return DMI_OK;
 }
 

@@ -36,20 +36,55 @@ struct ExactChunk
   ViewExact v[kExactChunk];
 };
 
-// One view, fast-path form (see tsdf_kernels.cu).
+// One view, fast-path form (see tsdf_fast.cu).  Every row is an affine function of the GLOBAL voxel
+// index: value(i,j,k) = r[0]*i + r[1]*j + r[2]*k + r[3], composed on the host in long double from
+// K * RT * gridMatrix * (orig + (idx + 0.5) * spacing).
+//   nx, ny  centred numerators  h.x - cxc*h.z,  h.y - cyc*h.z   (pixel = nx/hz + cxc)
+//   hz      homogeneous denominator h.z (CudaReconstruction.cu:176-184)
+//   cz      camera z = the "real depth" of CudaReconstruction.cu:207
 struct ViewFast
 {
-  double P[12];     // rows 0..2 of K * RT * G_affine: homogeneous pixel coords from VOXEL INDICES (i,j,k,1)
-  double Z[4];      // camera z from voxel indices (row 2 of RT * G_affine)
+  double nx[4], ny[4], hz[4], cz[4];
+  double m2;                      // T2 margin on s = nx - p*hz (2^-44 of the rows' magnitude bound)
+  double m2z;                     // T2 margin on hz
+  double gd;                      // | |diff| - Delta | below this -> exact tier
+  float fnx[4], fny[4], fhz[4], fcz[4];   // the same rows rounded to float ([3] unused: bases are per brick)
+  float lx, ly, lz, lc;           // bound on |local offset terms| of each row inside one brick
+  float zm;                       // |fz| <= zm: too close to the camera plane for the FP32 tier
+  float pad[3];
 };
 
-constexpr int kFastChunk = 128;   // views per launch of the fast kernel (16 KB parameters + exact copy in global)
+constexpr int kFastChunk = 64;    // views per launch: 64 * (248 + 192) B = 28 KB of kernel parameters
 struct FastChunk
 {
   int n;
-  int pad;
+  int cxc, cyc;                   // integer pixel offsets removed from the numerators
+  int pinhole;                    // every K of the chunk has last row 0 0 1 0: h.z == camera z
+  float umax1g;                   // largest centred |pixel| that can be in bounds, + 2 (fallback bound)
+  float k3;                       // E = k3 * ((|b| + 3 l) + U1 * (|bz| + 3 lz))
+  float kq;                       // T = 0.5 - U1 * kq - 2^-20
+  float delta_up;                 // float >= Delta * (1 + 2^-20)
   ViewFast v[kFastChunk];
+  ViewExact e[kFastChunk];
 };
+
+struct FastCounters               // optional diagnostics (device memory, may be null)
+{
+  unsigned long long t1_certified, t2_entered, t3_entered, delta_guard, units, culled, near_band, brick_views;
+};
+
+// Per-view data the fast kernel gathers from, built by launch_prepare_views:
+//   cls       float[n][H][W]   depth rounded to float, -1.0f exactly on the pixels that are invalid after
+//                              the best-cost filter (never -1.0f on a valid pixel)
+//   tileDmax  float[n][TH][TW] per 16x16 tile of storage rows: max valid depth (rounded up), -inf when the
+//                              tile has no valid pixel, +inf when it holds a NaN
+cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
+                                 float* d_cls, float* d_tileDmax, cudaStream_t s);
+cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
+                             const float* d_cls, const float* d_tileDmax, bool cull,
+                             void* d_vol, int scalarType, FastCounters* d_counters, cudaStream_t s);
+void compose_fast_view(const GridParams& g, const double* K16, const double* RT16, int cxc, int cyc, ViewFast* out);
+void fill_fast_chunk_constants(const GridParams& g, FastChunk* c);
 
 cudaError_t launch_tsdf_exact(const GridParams& g, const ExactChunk& c, const double* d_depths,
                               void* d_vol, int scalarType, cudaStream_t s);

@@ -1,0 +1,615 @@
+// Certified fast path of the TSDF integration for sm_100a.
+//
+// The reference evaluates ~78 FP64 operations per voxel*view (CudaReconstruction.cu:158-212), most
+// of them to find WHICH pixel the voxel centre rounds to and WHICH branch of the ray potential
+// applies.  Those answers are discrete, so they can be found cheaply and then PROVEN: this kernel
+// keeps every discrete decision of the reference (behind-camera test :177, pixel rounding :187-188,
+// bounds :192-197, depth == -1 :202 after the best-cost filter, the potential's branches :114-119)
+// bit-for-bit; only the continuous values (camera z, the linear branch) differ from the reference's
+// rounding by a few ulp of double.  Error bounds are derived in DESIGN.md ("certification").
+//
+// Per CTA: a brick of 16 x 8 x 8 voxels (4 warps of 8 x 4 lanes, 8 voxels per thread along k) and a
+// chunk of up to 64 views.
+//   pre-pass   one thread per view: FP64 brick base of the projective rows -> float; projected bounding
+//              box of the brick; CULL the view when every voxel is behind the camera, outside the image,
+//              over tiles without a valid pixel, or farther than Delta behind every valid depth of its
+//              footprint (all of which contribute exactly nothing); per-brick error scales; survivors
+//              are compacted in view order into shared memory.
+//   phase A    T1, FP32: 3 FFMA + MUFU.RCP + 2 FFMA give the centred pixel rounded by the magic-number
+//              add; 2 more FFMA its distance to the integer; certified when that distance is below
+//              0.5 - (E*r + c0).  Uncertified voxels (~0.1 %) go to
+//              T2, FP64: composed rows (9 DFMA) + residual test of the candidate and its neighbours, and
+//              T3, the reference's own operation sequence, when T2 meets a tie within 2^-44.
+//   phase B    gather of the FLOAT classification image (4 B per voxel*view)
+//   phase C    FP32: invalid / farther than Delta (certified with margin) -> add 0 or -Eta*Rho; the thin
+//              band around the surface re-gathers the double depth and evaluates the potential in FP64
+//              (T3 when |diff| is within 2^-44 of Delta, the potential's only discontinuity).
+// Views are accumulated in list order per voxel, like the reference's host loop (:343).
+#include "dmi_internal.cuh"
+#include "tsdf_device.cuh"
+
+#include <cmath>
+#include <climits>
+#include <algorithm>
+
+namespace dmi {
+
+constexpr int FM = 8;                       // voxels per thread, consecutive k
+constexpr int FBI = 16, FBJ = 8;            // brick = 16 x 8 x FM voxels = 4 warps of 8 x 4 lanes
+constexpr int FT = 128;
+constexpr int FSI = 4, FSJ = 4, FSK = 4;    // supertile = 64 x 32 x 32 voxels, enumerated contiguously
+constexpr float kMagic = 12582912.0f;       // 1.5 * 2^23: adding it rounds |x| < 2^22 to an integer
+constexpr int kMagicBits = 0x4B400000;
+constexpr int kTile = 16;                   // tile edge of the per-view tile statistics
+
+constexpr int kBad = INT_MIN + 2;           // every valid gather index (px - py*W) is above this
+constexpr int kReject = kBad - 1;           // certified: this voxel*view contributes nothing
+constexpr int kNeedExact = kBad - 2;        // could not certify: run T3
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+__device__ __forceinline__ double affine(const double* r, double di, double dj, double dk)
+{
+  return fma(di, r[0], fma(dj, r[1], fma(dk, r[2], r[3])));
+}
+
+// T3: the whole voxel*view update exactly as the reference does it.  By value in and out, so the
+// caller's accumulators stay in registers.
+template <typename T>
+__device__ __noinline__ T exact_unit(const GridParams* g, const ViewExact* e, const double* depth,
+                                     const float* cls, int i, int j, int k, T acc)
+{
+  double wx, wy, wz;
+  voxel_world(*g, i, j, k, wx, wy, wz);
+  integrate_exact<T>(*g, *e, depth, wx, wy, wz, acc, cls);
+  return acc;
+}
+
+// T2: FP64 certification of the T1 candidate (pu, pv: centred integer pixel as float).
+// Returns the gather index px - py*W (relative to the last storage row), kReject or kNeedExact.
+__device__ __forceinline__ int tier2(const ViewFast& V, int cxc, int cyc, int W, int H,
+                                     double di, double dj, double dk, float pu, float pv)
+{
+  const double hz = affine(V.hz, di, dj, dk);
+  if (!(hz > V.m2z)) return (hz < -V.m2z) ? kReject : kNeedExact;            // NaN -> exact
+  const double half = 0.5 * hz;
+  const double m2 = V.m2;
+  if (!(m2 < 0.01 * half)) return kNeedExact;
+  // the candidate is garbage when T1 overflowed; beyond 2^22 let the exact tier decide
+  double cu = (double)pu, cv = (double)pv;
+  if (!(fabs(cu) < 4194304.0 && fabs(cv) < 4194304.0)) return kNeedExact;
+  double su = fma(-cu, hz, affine(V.nx, di, dj, dk));                         // (u' - cu) * hz
+  double sv = fma(-cv, hz, affine(V.ny, di, dj, dk));
+  if (su >= half + m2) { cu += 1.0; su -= hz; } else if (su <= -half - m2) { cu -= 1.0; su += hz; }
+  if (sv >= half + m2) { cv += 1.0; sv -= hz; } else if (sv <= -half - m2) { cv -= 1.0; sv += hz; }
+  if (!(fabs(su) < half - m2 && fabs(sv) < half - m2)) return kNeedExact;     // tie, or T1 off by more than one
+  const int px = (int)cu + cxc, py = (int)cv + cyc;
+  if ((unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H) return px - py * W;
+  return kReject;
+}
+
+// Per-view record in shared memory, written by the pre-pass for the views that survive culling.
+struct __align__(16) ViewSm
+{
+  float4 base;      // brick base of nx, ny, hz (float), zm
+  float4 et;        // Ex, Ey, Tx, Ty: certified iff |eu| < Tx - Ex*r and |ev| < Ty - Ey*r
+  float4 cx;        // fnx[0..2], far threshold (Delta + margin)
+  float4 cy;        // fny[0..2], brick base of camera z (non-pinhole only)
+  float4 cz;        // fhz[0..2], -
+  float4 cc;        // fcz[0..2], - (non-pinhole only)
+  double czr[4];    // camera-z row (FP64)
+  double gd;
+  int view;
+  int pad;
+};
+
+struct BrickBox { bool valid; float ux, uy; int tx0, tx1, ty0, ty1; };
+
+// Projected bounding box of the brick for one view (8 corners; the projection of a box with hz > 0 is
+// the convex hull of its projected corners).  Returns false when the box cannot be trusted (brick too
+// close to the camera plane).  Margins: 1.5 px + the FP32 evaluation error (<= 0.25 px inside the
+// image by the E*r test, proportional to |u| outside).
+__device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c, float fbx, float fby, float fbz,
+                                          float zlo, int W, int H, BrickBox& o, bool& outside)
+{
+  outside = false;
+  const float Eg = c.k3 * (fmaxf(fabsf(fbx) + 3.f * V.lx, fabsf(fby) + 3.f * V.ly) + c.umax1g * (fabsf(fbz) + 3.f * V.lz));
+  if (!(zlo > V.zm) || !(Eg * (1.0f / zlo) <= 0.25f)) return false;
+  const float ei = (float)(FBI - 1), ej = (float)(FBJ - 1), ek = (float)(FM - 1);
+  const float zi = V.fhz[0] * ei, zj = V.fhz[1] * ej, zk = V.fhz[2] * ek;
+  const float xi = V.fnx[0] * ei, xj = V.fnx[1] * ej, xk = V.fnx[2] * ek;
+  const float yi = V.fny[0] * ei, yj = V.fny[1] * ej, yk = V.fny[2] * ek;
+  float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 8; q++)
+  {
+    const float hz = fbz + ((q & 1) ? zi : 0.f) + ((q & 2) ? zj : 0.f) + ((q & 4) ? zk : 0.f);
+    const float r = 1.0f / hz;
+    const float u = (fbx + ((q & 1) ? xi : 0.f) + ((q & 2) ? xj : 0.f) + ((q & 4) ? xk : 0.f)) * r;
+    const float w = (fby + ((q & 1) ? yi : 0.f) + ((q & 2) ? yj : 0.f) + ((q & 4) ? yk : 0.f)) * r;
+    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
+  }
+  if (!(umin == umin && umax == umax && vmin == vmin && vmax == vmax)) return false;    // NaN
+  const float kr = 0.3f / c.umax1g;
+  const float ulo = umin - (1.5f + kr * fabsf(umin)), uhi = umax + (1.5f + kr * fabsf(umax));
+  const float vlo = vmin - (1.5f + kr * fabsf(vmin)), vhi = vmax + (1.5f + kr * fabsf(vmax));
+  o.ux = fmaxf(fabsf(ulo), fabsf(uhi));
+  o.uy = fmaxf(fabsf(vlo), fabsf(vhi));
+  const float xlo = ulo + (float)c.cxc, xhi = uhi + (float)c.cxc, ylo = vlo + (float)c.cyc, yhi = vhi + (float)c.cyc;
+  if (!(xhi >= 0.f && xlo <= (float)(W - 1) && yhi >= 0.f && ylo <= (float)(H - 1))) { outside = true; return true; }
+  const int px0 = max(0, (int)floorf(xlo)), px1 = min(W - 1, (int)ceilf(xhi));
+  const int py0 = max(0, (int)floorf(ylo)), py1 = min(H - 1, (int)ceilf(yhi));
+  // storage rows are bottom-up: row = H-1-py
+  o.tx0 = px0 / kTile; o.tx1 = px1 / kTile; o.ty0 = (H - 1 - py1) / kTile; o.ty1 = (H - 1 - py0) / kTile;
+  o.valid = true;
+  return true;
+}
+
+template <typename T, bool PINHOLE, bool COUNT>
+__global__ void __launch_bounds__(FT)
+tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
+                 const double* __restrict__ depths, const float* __restrict__ cls,
+                 const float* __restrict__ tileDmax, int cull, T* __restrict__ vol,
+                 int nbi, int nbj, int nbk, int TW, int TH, FastCounters* counters)
+{
+  static_assert(kFastChunk <= FT, "one pre-pass thread per view");
+  __shared__ ViewSm s_view[kFastChunk];
+  __shared__ int s_cnt[FT / 32];
+
+  // ---- brick decode (CTA-uniform)
+  constexpr unsigned per = FSI * FSJ * FSK;
+  const unsigned st = blockIdx.x / per, rr = blockIdx.x % per;
+  const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ;
+  const int bi = (st % nsi) * FSI + rr % FSI;
+  const int bj = ((st / nsi) % nsj) * FSJ + (rr / FSI) % FSJ;
+  const int bk = (st / (nsi * nsj)) * FSK + rr / (FSI * FSJ);
+  if (bi >= nbi || bj >= nbj || bk >= nbk) return;
+  const int i0 = bi * FBI, j0 = bj * FBJ, k0 = g.k0 + bk * FM;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int W = g.W, H = g.H;
+
+  // ---- pre-pass: thread v prepares view v
+  {
+    const int v = threadIdx.x;
+    bool keep = false;
+    float fbx = 0.f, fby = 0.f, fbz = 0.f, fbc = 0.f, Ux = c.umax1g, Uy = c.umax1g, czmaxabs = 0.f;
+    if (v < c.n)
+    {
+      const ViewFast& V = c.v[v];
+      fbx = __double2float_rn(affine(V.nx, (double)i0, (double)j0, (double)k0));
+      fby = __double2float_rn(affine(V.ny, (double)i0, (double)j0, (double)k0));
+      fbz = __double2float_rn(affine(V.hz, (double)i0, (double)j0, (double)k0));
+      fbc = PINHOLE ? fbz : __double2float_rn(affine(V.cz, (double)i0, (double)j0, (double)k0));
+      const float ei = (float)(FBI - 1), ej = (float)(FBJ - 1), ek = (float)(FM - 1);
+      // range of h.z and of camera z over the brick (affine: extremes are sums of per-axis extremes)
+      const float zi = V.fhz[0] * ei, zj = V.fhz[1] * ej, zk = V.fhz[2] * ek;
+      const float zslack = 4e-7f * (fabsf(fbz) + 3.f * V.lz);
+      const float zlo = fbz + fminf(zi, 0.f) + fminf(zj, 0.f) + fminf(zk, 0.f) - zslack;
+      const float zhi = fbz + fmaxf(zi, 0.f) + fmaxf(zj, 0.f) + fmaxf(zk, 0.f) + zslack;
+      float clo = zlo, chi = zhi;
+      if (!PINHOLE)
+      {
+        const float ci = V.fcz[0] * ei, cj = V.fcz[1] * ej, ck = V.fcz[2] * ek;
+        const float cslack = 4e-7f * (fabsf(fbc) + 3.f * V.lc);
+        clo = fbc + fminf(ci, 0.f) + fminf(cj, 0.f) + fminf(ck, 0.f) - cslack;
+        chi = fbc + fmaxf(ci, 0.f) + fmaxf(cj, 0.f) + fmaxf(ck, 0.f) + cslack;
+      }
+      czmaxabs = fmaxf(fabsf(clo), fabsf(chi));
+      keep = true;
+      BrickBox box; box.valid = false;
+      bool outside = false;
+      const bool boxed = brick_box(V, c, fbx, fby, fbz, zlo, W, H, box, outside);
+      if (boxed) { Ux = fminf(c.umax1g, box.ux + 1.f); Uy = fminf(c.umax1g, box.uy + 1.f); }
+      if (cull)
+      {
+        if (zhi < -V.zm) keep = false;                        // the whole brick is behind the camera (:177)
+        else if (boxed && outside) keep = false;              // ... projects outside the image (:192-197)
+        else if (boxed && box.valid && (box.tx1 - box.tx0 + 1) * (box.ty1 - box.ty0 + 1) <= 64)
+        {
+          const float* td = tileDmax + (size_t)v * TW * TH;
+          float dmax = -INFINITY;
+          for (int ty = box.ty0; ty <= box.ty1; ty++)
+            for (int tx = box.tx0; tx <= box.tx1; tx++) dmax = fmaxf(dmax, __ldg(td + ty * TW + tx));
+          const float thr = c.delta_up + 1e-6f * czmaxabs;
+          // no valid pixel under the brick (:202), or every voxel farther than Delta BEHIND every valid
+          // depth it can meet: rayPotential returns 0 (:114-115)
+          if (dmax == -INFINITY || clo - dmax > thr) keep = false;
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_cnt[w] = __popc(bal);
+    __syncthreads();
+    if (keep)
+    {
+      int pos = __popc(bal & ((1u << lane) - 1u));
+      for (int q = 0; q < w; q++) pos += s_cnt[q];
+      const ViewFast& V = c.v[v];
+      ViewSm& S = s_view[pos];
+      const float Ex = c.k3 * ((fabsf(fbx) + 3.f * V.lx) + Ux * (fabsf(fbz) + 3.f * V.lz));
+      const float Ey = c.k3 * ((fabsf(fby) + 3.f * V.ly) + Uy * (fabsf(fbz) + 3.f * V.lz));
+      S.base = make_float4(fbx, fby, fbz, V.zm);
+      S.et = make_float4(Ex, Ey, 0.5f - (Ux * c.kq + 9.6e-7f), 0.5f - (Uy * c.kq + 9.6e-7f));
+      S.cx = make_float4(V.fnx[0], V.fnx[1], V.fnx[2], c.delta_up + 1e-6f * czmaxabs);
+      S.cy = make_float4(V.fny[0], V.fny[1], V.fny[2], fbc);
+      S.cz = make_float4(V.fhz[0], V.fhz[1], V.fhz[2], 0.f);
+      S.cc = make_float4(V.fcz[0], V.fcz[1], V.fcz[2], 0.f);
+      S.czr[0] = V.cz[0]; S.czr[1] = V.cz[1]; S.czr[2] = V.cz[2]; S.czr[3] = V.cz[3];
+      S.gd = V.gd;
+      S.view = v;
+    }
+  }
+  int nsurv = 0;
+#pragma unroll
+  for (int q = 0; q < FT / 32; q++) nsurv += s_cnt[q];
+  if (COUNT && counters && threadIdx.x == 0)
+  {
+    atomicAdd(&counters->culled, (unsigned long long)(c.n - nsurv));
+    atomicAdd(&counters->brick_views, (unsigned long long)c.n);
+  }
+  if (nsurv == 0) return;                                     // the brick's voxels are not even read
+  __syncthreads();
+
+  const int li = (w & 1) * 8 + (lane & 7), lj = (w >> 1) * 4 + (lane >> 3);
+  const int i = i0 + li, j = j0 + lj;
+  if (i >= g.Nx || j >= g.Ny) return;                         // no barrier below
+  const float fli = (float)li, flj = (float)lj;
+  const double di = (double)i, dj = (double)j, dk0 = (double)k0;
+  // voxels beyond the slab's last plane (m >= nk) are computed and discarded: no divergence in the loop
+  const int nk = min(FM, g.k1 - k0);
+
+  T acc[FM];
+  const size_t plane = (size_t)g.Nx * g.Ny;
+  T* p = vol + ((size_t)(k0 - g.k0) * g.Ny + j) * g.Nx + i;
+#pragma unroll
+  for (int m = 0; m < FM; m++) acc[m] = (m < nk) ? p[m * plane] : (T)0;
+
+  const size_t npix = (size_t)W * H;
+  const int pxoff = kMagicBits - c.cxc, pyoff = kMagicBits - c.cyc;
+  const double delta = g.delta, thick = g.thick;
+  const T nerT = (T)g.neg_eta_rho;
+  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0;
+
+  for (int q = 0; q < nsurv; q++)
+  {
+    const ViewSm& S = s_view[q];
+    const float4 b = S.base, et = S.et, cx = S.cx, cy = S.cy, cz = S.cz;
+    const int v = S.view;
+    // one rounding at base magnitude here, one in the per-voxel FFMA (delta_n = 3 * 2^-24 * ...)
+    const float fnx0 = b.x + fmaf(fli, cx.x, flj * cx.y);
+    const float fny0 = b.y + fmaf(fli, cy.x, flj * cy.y);
+    const float fhz0 = b.z + fmaf(fli, cz.x, flj * cz.y);
+    float fcz0 = 0.f, kc = 0.f;
+    if (!PINHOLE) { const float4 cc = S.cc; fcz0 = cy.w + fmaf(fli, cc.x, flj * cc.y); kc = cc.z; }
+    const float kx = cx.z, ky = cy.z, kz = cz.z;
+    const float zm = b.w, thrfar = cx.w;
+    // storage row (H-1-py) of the bottom-up image (CudaReconstruction.cu:141-149): index = px - py*W from here
+    const size_t voff = npix * v + (size_t)(H - 1) * W;
+    const float* cv = cls + voff;
+    const double* dv = depths + voff;
+    asm volatile("" : "+l"(cv), "+l"(dv));                    // keep them as plain 64-bit registers
+
+    // ---- phase A: classify all FM voxels with the FP32 tier
+    int idx[FM];
+    unsigned need = 0;
+    bool anyv = false;
+#pragma unroll
+    for (int m = 0; m < FM; m++)
+    {
+      const float fz = fmaf((float)m, kz, fhz0);
+      const float fx = fmaf((float)m, kx, fnx0);
+      const float fy = fmaf((float)m, ky, fny0);
+      const float r = rcp_approx(fz);
+      const float tu = fmaf(fx, r, kMagic), tv = fmaf(fy, r, kMagic);      // centred pixel, rounded to integer
+      const float pu = tu - kMagic, pv = tv - kMagic;
+      const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);            // distance to that integer
+      const float tx = fmaf(-et.x, r, et.z), ty = fmaf(-et.y, r, et.w);
+      const bool cert = (fz > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
+      const int px = __float_as_int(tu) - pxoff;
+      const int py = __float_as_int(tv) - pyoff;
+      const bool ok = cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H;
+      idx[m] = ok ? px - py * W : kReject;
+      anyv |= ok;
+      if (!cert) need |= 1u << m;
+      if (COUNT) n_t1 += cert ? 1 : 0;
+    }
+    // ---- rare: voxels the FP32 tier could not certify (and every voxel behind the camera plane).
+    // Dynamic m, so that lanes with different m run the same instructions together.
+    if (need)
+    {
+      unsigned need3 = 0;
+      while (need)
+      {
+        const int m = __ffs(need) - 1;
+        need &= need - 1;
+        const float fm = (float)m;
+        const float fz = fmaf(fm, kz, fhz0);
+        int id = kReject;                                                    // certified behind the camera
+        if (!(fz < -zm))
+        {
+          if (COUNT) n_t2++;
+          const float r = rcp_approx(fz);
+          const float pu = fmaf(fmaf(fm, kx, fnx0), r, kMagic) - kMagic, pv = fmaf(fmaf(fm, ky, fny0), r, kMagic) - kMagic;
+          id = tier2(c.v[v], c.cxc, c.cyc, W, H, di, dj, dk0 + (double)m, pu, pv);
+          if (id == kNeedExact) { need3 |= 1u << m; id = kReject; }
+        }
+#pragma unroll
+        for (int mm = 0; mm < FM; mm++) if (mm == m) idx[mm] = id;
+        anyv |= id > kBad;
+      }
+      if (need3)
+      {
+#pragma unroll
+        for (int m = 0; m < FM; m++)
+          if (need3 & (1u << m))
+          {
+            if (COUNT) n_t3++;
+            acc[m] = exact_unit<T>(&g, &c.e[v], depths + npix * v, cls + npix * v, i, j, k0 + m, acc[m]);
+          }
+      }
+    }
+    if (!anyv) continue;
+
+    // ---- phase B: all gathers of the float classification image in flight together
+    float d32[FM];
+#pragma unroll
+    for (int m = 0; m < FM; m++) d32[m] = (idx[m] > kBad) ? __ldg(cv + idx[m]) : -1.0f;
+
+    // ---- phase C: FP32 classification; -1.0f = invalid after the filter (:202)
+    unsigned near = 0;
+#pragma unroll
+    for (int m = 0; m < FM; m++)
+    {
+      const float fc = PINHOLE ? fmaf((float)m, kz, fhz0) : fmaf((float)m, kc, fcz0);   // camera z (:207)
+      const float df = fc - d32[m];
+      const bool valid = d32[m] != -1.0f;
+      const bool far = fabsf(df) > thrfar;                                   // certainly |diff| > Delta (:114)
+      if (valid && far && df < 0.f) acc[m] += nerT;                          // in front: -Eta*Rho; behind: 0 (:115)
+      if (valid && !far) near |= 1u << m;                                    // NaN lands here too
+    }
+    // ---- the band around the surface: double depth, FP64 potential
+    if (near)
+    {
+      const double zij = __fma_rn(di, S.czr[0], __fma_rn(dj, S.czr[1], S.czr[3]));
+      const double czk = S.czr[2], gd = S.gd;
+#pragma unroll
+      for (int m = 0; m < FM; m++)
+      {
+        if (near & (1u << m))
+        {
+          if (COUNT) n_nb++;
+          // explicit roundings: the value of a voxel must not depend on which unrolled copy (m) or
+          // brick decomposition evaluates it, so that z-slabs concatenate bit-identically
+          const double d = __ldg(dv + idx[m]);
+          const double z = __fma_rn(dk0 + (double)m, czk, zij);              // :207, from GLOBAL indices
+          const double diff = __dsub_rn(z, d);
+          const double ad = fabs(diff);
+          const double td = __dsub_rn(ad, delta);
+          if (fabs(td) < gd)
+          {
+            if (COUNT) n_dg++;
+            acc[m] = exact_unit<T>(&g, &c.e[v], depths + npix * v, cls + npix * v, i, j, k0 + m, acc[m]);
+          }
+          else if (td > 0.0)
+          {
+            if (!(diff > 0.0)) acc[m] += nerT;                               // :114-115
+          }
+          else
+          {
+            const double res = (ad > thick) ? (diff > 0.0 ? g.rho : -g.rho)  // :116-117
+                                            : __dmul_rn(g.rho_over_thick, diff);   // :118-119
+            acc[m] = add_rn(acc[m], (T)res);                                  // :211
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < FM; m++)
+    if (m < nk) p[m * plane] = acc[m];
+
+  if (COUNT && counters)
+  {
+    atomicAdd(&counters->t1_certified, n_t1);
+    atomicAdd(&counters->t2_entered, n_t2);
+    atomicAdd(&counters->t3_entered, n_t3);
+    atomicAdd(&counters->delta_guard, n_dg);
+    atomicAdd(&counters->near_band, n_nb);
+    atomicAdd(&counters->units, (unsigned long long)FM * nsurv);
+  }
+}
+
+template <typename T, bool PINHOLE>
+static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths,
+                           const float* d_cls, const float* d_tileDmax, bool cull, T* d_vol, int nbi, int nbj,
+                           int nbk, int TW, int TH, FastCounters* d_counters, cudaStream_t s)
+{
+  if (d_counters)
+    tsdf_fast_kernel<T, PINHOLE, true><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, cull ? 1 : 0, d_vol, nbi, nbj, nbk, TW, TH, d_counters);
+  else
+    tsdf_fast_kernel<T, PINHOLE, false><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, cull ? 1 : 0, d_vol, nbi, nbj, nbk, TW, TH, nullptr);
+}
+
+cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
+                             const float* d_cls, const float* d_tileDmax, bool cull,
+                             void* d_vol, int scalarType, FastCounters* d_counters, cudaStream_t s)
+{
+  const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
+  if (nbi <= 0 || nbj <= 0 || nbk <= 0 || c.n <= 0) return cudaSuccess;
+  const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
+  const unsigned grid = nsi * nsj * nsk * (FSI * FSJ * FSK);
+  const int TW = (g.W + kTile - 1) / kTile, TH = (g.H + kTile - 1) / kTile;
+  if (scalarType == 1)
+  {
+    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (double*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
+    else launch_variant<double, false>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (double*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
+  }
+  else
+  {
+    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (float*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
+    else launch_variant<float, false>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (float*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
+  }
+  return cudaGetLastError();
+}
+
+// ---- view preparation: best-cost filter (ReconstructionData.cxx:159-166) folded into a float
+// classification image, plus per-tile statistics for the brick culling.  One warp per 16x16 tile of
+// storage rows, each lane 8 consecutive pixels; a single HBM-bound pass over the maps.
+__global__ void __launch_bounds__(256)
+prepare_views_kernel(const double* __restrict__ depths, const double* __restrict__ cost, double thr,
+                     int nViews, int W, int H, int TW, int TH, float* __restrict__ cls, float* __restrict__ tileDmax)
+{
+  const int lane = threadIdx.x & 31;
+  const size_t tile = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t tilesPerView = (size_t)TW * TH;
+  if (tile >= tilesPerView * nViews) return;
+  const int v = (int)(tile / tilesPerView);
+  const int t = (int)(tile % tilesPerView);
+  const int ty = t / TW, tx = t % TW;
+  const int row = ty * kTile + (lane >> 1), col = tx * kTile + (lane & 1) * 8;
+  float dmax = -INFINITY;
+  if (row < H)
+  {
+    const size_t base = (size_t)v * W * H + (size_t)row * W;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+    {
+      if (col + q < W)
+      {
+        const double d = __ldg(depths + base + col + q);
+        const bool invalid = (d == -1.0) || (cost && __ldg(cost + base + col + q) > thr);
+        float f = -1.0f;
+        if (!invalid)
+        {
+          f = __double2float_rn(d);
+          if (f == -1.0f) f = (d < -1.0) ? -1.00000012f : -0.99999994f;       // never -1.0f on a valid pixel
+          // tile maximum, rounded up; NaN poisons the tile (+inf: never culled as "far behind")
+          float up = f;
+          if ((double)up < d) up = __int_as_float(__float_as_int(up) + (up >= 0.f ? 1 : -1));
+          dmax = (d != d) ? INFINITY : fmaxf(dmax, up);
+        }
+        cls[base + col + q] = f;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (lane == 0) tileDmax[tile] = dmax;
+}
+
+cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
+                                 float* d_cls, float* d_tileDmax, cudaStream_t s)
+{
+  const int TW = (W + kTile - 1) / kTile, TH = (H + kTile - 1) / kTile;
+  const size_t tiles = (size_t)TW * TH * nViews;
+  if (tiles == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((tiles + 7) / 8);
+  prepare_views_kernel<<<blocks, 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, TW, TH, d_cls, d_tileDmax);
+  return cudaGetLastError();
+}
+
+// ---- host side: composition of the per-view affine rows ----------------------------------------
+
+static float up(double x)      // a float >= x (x >= 0)
+{
+  float f = (float)x;
+  if ((double)f < x) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+void fill_fast_chunk_constants(const GridParams& g, FastChunk* c)
+{
+  c->cxc = g.W / 2;
+  c->cyc = g.H / 2;
+  // in-bounds centred pixels satisfy |u'| <= max(W, H) / 2 + 0.5
+  c->umax1g = up(std::max(g.W, g.H) / 2.0 + 2.0);
+  // E = (4/3) * 3 * 2^-24 * (1 + 1%) * (...)
+  c->k3 = up(4.04 * std::ldexp(1.0, -24));
+  // c0 = (4/3) * U1 * 2^-23 * 1.05 (MUFU.RCP: 1 ulp), + 2^-20 of slack for the float arithmetic of the test
+  c->kq = up((4.0 / 3.0) * 1.05 * std::ldexp(1.0, -23));
+  c->delta_up = up(g.delta * (1.0 + std::ldexp(1.0, -20)));
+}
+
+// rows as affine functions of the global voxel index, in long double
+void compose_fast_view(const GridParams& g, const double* K16, const double* RT16, int cxc, int cyc, ViewFast* out)
+{
+  typedef long double L;
+  // world = Gm * (orig + (idx + 0.5) * sp) + Gt  ->  WA (3x3) * idx + Wb
+  L WA[3][3], Wb[3];
+  for (int r = 0; r < 3; r++)
+  {
+    Wb[r] = (L)g.gm[4 * r + 3];
+    for (int a = 0; a < 3; a++)
+    {
+      WA[r][a] = (L)g.gm[4 * r + a] * (L)g.sp[a];
+      Wb[r] += (L)g.gm[4 * r + a] * ((L)g.orig[a] + (L)0.5 * (L)g.sp[a]);
+    }
+  }
+  // cam = R * world + T
+  L CA[3][3], Cb[3];
+  for (int r = 0; r < 3; r++)
+  {
+    Cb[r] = (L)RT16[4 * r + 3];
+    for (int a = 0; a < 3; a++)
+    {
+      CA[r][a] = 0;
+      for (int q = 0; q < 3; q++) CA[r][a] += (L)RT16[4 * r + q] * WA[q][a];
+      Cb[r] += (L)RT16[4 * r + a] * Wb[a];
+    }
+  }
+  // h = K(3x4) * (cam, 1)
+  L HA[3][3], Hb[3];
+  for (int r = 0; r < 3; r++)
+  {
+    Hb[r] = (L)K16[4 * r + 3];
+    for (int a = 0; a < 3; a++)
+    {
+      HA[r][a] = 0;
+      for (int q = 0; q < 3; q++) HA[r][a] += (L)K16[4 * r + q] * CA[q][a];
+      Hb[r] += (L)K16[4 * r + a] * Cb[a];
+    }
+  }
+  const L cc[2] = {(L)cxc, (L)cyc};
+  double* rows[2] = {out->nx, out->ny};
+  for (int r = 0; r < 2; r++)
+  {
+    for (int a = 0; a < 3; a++) rows[r][a] = (double)(HA[r][a] - cc[r] * HA[2][a]);
+    rows[r][3] = (double)(Hb[r] - cc[r] * Hb[2]);
+  }
+  for (int a = 0; a < 3; a++) { out->hz[a] = (double)HA[2][a]; out->cz[a] = (double)CA[2][a]; }
+  out->hz[3] = (double)Hb[2];
+  out->cz[3] = (double)Cb[2];
+  for (int a = 0; a < 4; a++)
+  {
+    out->fnx[a] = (float)out->nx[a]; out->fny[a] = (float)out->ny[a];
+    out->fhz[a] = (float)out->hz[a]; out->fcz[a] = (float)out->cz[a];
+  }
+
+  // magnitude bounds over the whole grid (global indices 0..N-1), for the FP64 margins
+  const double im[3] = {(double)std::max(g.Nx - 1, 0), (double)std::max(g.Ny - 1, 0), (double)std::max(g.Nz - 1, 0)};
+  auto S = [&](const double* r) { return std::fabs(r[0]) * im[0] + std::fabs(r[1]) * im[1] + std::fabs(r[2]) * im[2] + std::fabs(r[3]); };
+  // the reference evaluates h.x = K00*cx + K01*cy + K02*cz + K03 etc.: its intermediate magnitudes are
+  // bounded by S(nx) + cxc*S(hz) (same for y); 2^-44 of that covers both evaluation orders many times over
+  const double umax = std::max(g.W, g.H) / 2.0 + 2.0;
+  const double Sx = S(out->nx) + std::fabs((double)cxc) * S(out->hz);
+  const double Sy = S(out->ny) + std::fabs((double)cyc) * S(out->hz);
+  out->m2 = std::ldexp(1.0, -44) * (std::max(Sx, Sy) + umax * S(out->hz));
+  out->m2z = std::ldexp(1.0, -44) * S(out->hz);
+  out->gd = std::ldexp(1.0, -44) * (S(out->cz) + 1.0 + std::fabs(g.delta));
+  // local offsets inside one brick
+  auto Lb = [&](const double* r) { return up(std::fabs(r[0]) * (FBI - 1) + std::fabs(r[1]) * (FBJ - 1) + std::fabs(r[2]) * (FM - 1)); };
+  out->lx = Lb(out->nx); out->ly = Lb(out->ny); out->lz = Lb(out->hz); out->lc = Lb(out->cz);
+  // fz > zm must imply dz/fz <= 1/4 with dz <= 3.03 * 2^-24 * (|hz| + 3 lz): zm = 12.5 * 2^-24 * max(...)
+  out->zm = up(12.5 * std::ldexp(1.0, -24) * (S(out->hz) + 3.0 * (double)out->lz));
+  out->pad[0] = out->pad[1] = out->pad[2] = 0.f;
+}
+
+}  // namespace dmi

@@ -15,6 +15,7 @@
 // Views are added in list order per voxel, like the reference's host loop (:343), so the floating
 // point accumulation order is the reference's.
 #include "dmi_internal.cuh"
+#include "tsdf_device.cuh"
 
 namespace dmi {
 
@@ -44,68 +45,6 @@ static inline unsigned brick_grid_size(int nbi, int nbj, int nbk)
 {
   const unsigned nsi = (nbi + SI - 1) / SI, nsj = (nbj + SJ - 1) / SJ, nsk = (nbk + SK - 1) / SK;
   return nsi * nsj * nsk * (SI * SJ * SK);
-}
-
-// ---- the reference's arithmetic, operation for operation ---------------------------------------
-// transformFrom4Matrix (CudaReconstruction.cu:88-93): m0*x + m1*y + m2*z + m3, left to right.
-// The intrinsics forbid FMA contraction, i.e. the numerics of the shipped -G build.
-__device__ __forceinline__ double row_point(const double* m, double x, double y, double z)
-{
-  return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), __dmul_rn(m[2], z)), m[3]);
-}
-
-// rayPotential<T> (CudaReconstruction.cu:105-120).  `sign` there is (int)(diff/|diff|) = +-1 for any
-// finite non-zero diff and 0 for diff == 0, so rho*sign is copysign(rho, diff) or 0.
-template <typename T>
-__device__ __forceinline__ T ray_potential(const GridParams& g, double realDistance, double depthMapDistance)
-{
-  const double diff = __dsub_rn(realDistance, depthMapDistance);
-  const double a = fabs(diff);
-  T res;
-  if (a > g.delta)
-    res = (T)(diff > 0 ? 0.0 : g.neg_eta_rho);
-  else if (a > g.thick)
-    res = (T)(diff > 0 ? g.rho : (diff < 0 ? -g.rho : __dmul_rn(g.rho, 0.0)));
-  else
-    res = (T)__dmul_rn(g.rho_over_thick, diff);
-  return res;
-}
-
-// One voxel, one view, exactly as depthMapKernel does it from the world-space voxel centre on
-// (CudaReconstruction.cu:170-211).  (wx,wy,wz) is view-invariant and is computed once per voxel.
-template <typename T>
-__device__ __forceinline__ void integrate_exact(const GridParams& g, const ViewExact& V,
-                                                const double* __restrict__ depth,
-                                                double wx, double wy, double wz, T& acc)
-{
-  const double cx = row_point(V.RT + 0, wx, wy, wz);
-  const double cy = row_point(V.RT + 4, wx, wy, wz);
-  const double cz = row_point(V.RT + 8, wx, wy, wz);
-  const double hx = row_point(V.K + 0, cx, cy, cz);
-  const double hy = row_point(V.K + 4, cx, cy, cz);
-  const double hz = row_point(V.K + 8, cx, cy, cz);
-  if (hz < 0) return;                                   // :177
-  const double u = __ddiv_rn(hx, hz);                   // :183
-  const double v = __ddiv_rn(hy, hz);                   // :184
-  const int px = __double2int_rz(round(u));             // :187 (cvt.rzi.s32.f64: saturating, NaN -> INT_MIN)
-  const int py = __double2int_rz(round(v));             // :188
-  if (px < 0 || py < 0 || px >= g.W || py >= g.H) return;   // :192-197
-  const double d = __ldg(depth + (size_t)g.W * (size_t)(g.H - 1 - py) + px);   // :141-149, :201
-  if (d == -1) return;                                  // :202
-  acc += ray_potential<T>(g, cz, d);                    // :207-211
-}
-
-// Voxel centre in world space: computeVoxelCenter + transformFrom4Matrix(c_gridMatrix, ...)
-// (CudaReconstruction.cu:78-83, :168), with GLOBAL indices so z-slabs reproduce the full grid.
-__device__ __forceinline__ void voxel_world(const GridParams& g, int i, int j, int k,
-                                            double& wx, double& wy, double& wz)
-{
-  const double x = __dadd_rn(g.orig[0], __dmul_rn((double)i + 0.5, g.sp[0]));
-  const double y = __dadd_rn(g.orig[1], __dmul_rn((double)j + 0.5, g.sp[1]));
-  const double z = __dadd_rn(g.orig[2], __dmul_rn((double)k + 0.5, g.sp[2]));
-  wx = row_point(g.gm + 0, x, y, z);
-  wy = row_point(g.gm + 4, x, y, z);
-  wz = row_point(g.gm + 8, x, y, z);
 }
 
 template <typename T, int M>

@@ -75,7 +75,11 @@ class Context:
 
     # -- plumbing ------------------------------------------------------------------------------
     def set_stream(self, cuda_stream: int | None):
-        self._ck(self._lib.dmi_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """Run on the given cudaStream_t handle (0 = legacy default stream); None = the context's own stream."""
+        if cuda_stream is None:
+            self._ck(self._lib.dmi_use_own_stream(self._h))
+        else:
+            self._ck(self._lib.dmi_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def synchronize(self):
         self._ck(self._lib.dmi_synchronize(self._h))
@@ -166,6 +170,12 @@ class Context:
         n = C.c_longlong()
         self._ck(self._lib.dmi_tsdf_kernel_stats(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def tsdf_tier_counters(self):
+        out = (C.c_ulonglong * 8)()
+        self._ck(self._lib.dmi_tsdf_tier_counters(self._h, out))
+        return dict(zip(("t1_certified", "t2_entered", "t3_entered", "delta_guard", "units", "culled_brick_views",
+                         "near_band", "brick_views"), [int(x) for x in out]))
 
     # -- coloration ------------------------------------------------------------------------------
     def colorize(self, xyz: np.ndarray, colors: np.ndarray, K, RT, width: int, height: int):

@@ -60,6 +60,8 @@ extern "C" {
 
 #define DMI_OPT_TSDF_KERNEL 1
 #define DMI_OPT_VIEW_CHUNK 2         /* views per launch (0 = auto) */
+#define DMI_OPT_TIER_COUNTERS 3      /* 1: count tier decisions of the fast kernel (diagnostic build of the kernel) */
+#define DMI_OPT_CULL 4               /* 1 (default): skip (brick, view) pairs that provably contribute nothing */
 
 typedef struct dmi_ctx dmi_ctx;
 
@@ -73,8 +75,10 @@ int dmi_create(int device, dmi_ctx** ctx);
 int dmi_destroy(dmi_ctx* ctx);
 const char* dmi_last_error(const dmi_ctx* ctx);
 /* Run the context's work on an existing CUDA stream (a cudaStream_t passed as void*), e.g. the
- * caller's framework stream; NULL restores the context's own stream. */
+ * caller's framework stream.  NULL is the legacy default stream, as in the CUDA runtime.
+ * dmi_use_own_stream goes back to the non-blocking stream the context created for itself. */
 int dmi_set_stream(dmi_ctx* ctx, void* cuda_stream);
+int dmi_use_own_stream(dmi_ctx* ctx);
 int dmi_synchronize(dmi_ctx* ctx);
 int dmi_set_option(dmi_ctx* ctx, int option, long long value);
 
@@ -128,6 +132,13 @@ int dmi_apply_depth_threshold_device(dmi_ctx* ctx, size_t count, double* d_depth
 /* Device time (ms, CUDA events on the context's stream) and launch count of the integration kernels
  * issued since the last call to this function. */
 int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
+
+/* Diagnostics of the certified fast path (DMI_OPT_TIER_COUNTERS = 1): out[0] voxel*views certified by
+ * the FP32 tier, [1] sent to the FP64 tier, [2] sent to the exact tier, [3] exact because |diff| was
+ * within the guard band of Delta, [4] voxel*views processed after culling, [5] (brick, view) pairs
+ * culled, [6] voxel*views in the FP64 band around the surface, [7] (brick, view) pairs seen.
+ * Reading resets the counters. */
+int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[8]);
 
 /* ---- mesh coloration ----------------------------------------------------------------------- */
 

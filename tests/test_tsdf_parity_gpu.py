@@ -125,6 +125,32 @@ def test_view_chunking_does_not_change_results(gpu_ctx, kernel):
     assert np.array_equal(a, b)
 
 
+def test_brick_culling_is_conservative(gpu_ctx, oracle):
+    """Skipping (brick, view) pairs that cannot contribute must not change a single bit; checked with the
+    tier counters that pairs really were culled (cameras at radius 3 see the 2.4-box well inside a 640x480
+    image, whose background and thresholded tiles are invalid)."""
+    s = Scene(96, 12, 640, 480, rotate_deg=30.0, depth_noise=0.25)
+    ctx = gpu_ctx
+    outs = []
+    for cull in (1, 0):
+        ctx.set_option(_lib.DMI_OPT_CULL, cull)
+        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 1)
+        try:
+            outs.append(run_gpu(ctx, s, np.float64))
+            counters = ctx.tsdf_tier_counters()
+        finally:
+            ctx.set_option(_lib.DMI_OPT_CULL, 1)
+            ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 0)
+        if cull:
+            assert counters["culled_brick_views"] > 0
+        else:
+            assert counters["culled_brick_views"] >= 0
+    assert np.array_equal(outs[0], outs[1])
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    assert np.array_equal(outs[0] != 0, want != 0)
+    assert_close(outs[0], want)
+
+
 def edge_scene():
     """Voxel exactly at the camera centre (0/0 -> NaN pixel), h.z == 0 (+-inf pixel), voxels behind the
     camera, projections exactly on x.5, depth == -1, an all-invalid view.  Everything is exact in binary."""
