@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--kernel", default="auto", choices=["auto", "exact"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
+    ap.add_argument("--counters", action="store_true", help="print the fast kernel's tier counters to stderr (slower kernel build)")
     ap.add_argument("--group", type=int, default=40, help="views per all-gather group (N>1)")
     return ap.parse_args()
 
@@ -210,6 +212,9 @@ def main():
     ctx = Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_EXACT if args.kernel == "exact" else _lib.DMI_TSDF_KERNEL_AUTO)
+    ctx.set_option(_lib.DMI_OPT_CULL, args.cull)
+    if args.counters:
+        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 1)
     ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
     ctx.set_slab(k0, k1)
 
@@ -349,6 +354,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     kernel_ms, kernel_launches = ctx.tsdf_kernel_stats()
     launches = ctx.launch_counter() - launches0
+    if args.counters and args.kernel != "exact":
+        print("tier counters (rank %d): %s" % (rank, ctx.tsdf_tier_counters()), file=sys.stderr)
     value = units / (ms_step * 1e-3)
 
     # ---- end to end through the host-pointer ABI

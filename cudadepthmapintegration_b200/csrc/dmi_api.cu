@@ -79,7 +79,7 @@ struct dmi_ctx
   long long opt_kernel = DMI_TSDF_KERNEL_AUTO, opt_chunk = 0;
   long long total_launches = 0;
   dmi::FastChunk fast_chunk{};
-  DevBuf counters, cls, tiles;
+  DevBuf counters, cls, tiles, viewscratch;
   bool counters_on = false;
   bool opt_cull = true;
   std::string err;
@@ -165,7 +165,7 @@ int dmi_destroy(dmi_ctx* ctx)
   }
   ctx->filtered.release();
   ctx->counters.release();
-  ctx->cls.release(); ctx->tiles.release();
+  ctx->cls.release(); ctx->tiles.release(); ctx->viewscratch.release();
   ctx->c_xyz.release(); ctx->c_colors.release(); ctx->c_mats.release();
   ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release();
   ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
@@ -333,15 +333,16 @@ static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_dep
 {
   const dmi::GridParams& g = ctx->g;
   const size_t npix = (size_t)g.W * g.H;
-  const size_t tilesPerView = (size_t)((g.W + 15) / 16) * ((g.H + 15) / 16);
+  const size_t tilesPerView = (size_t)dmi::tile_pyramid_layout(g.W, g.H).perView;
   int chunk = dmi::kFastChunk;
   if (ctx->opt_chunk > 0 && ctx->opt_chunk < chunk) chunk = (int)ctx->opt_chunk;
   // views prepared at a time: whole chunks, about 1 GB of classification image
   int group = (int)std::max<size_t>(1, (1ull << 30) / (npix * 4));
   group = std::max(chunk, group / chunk * chunk);
   group = std::min(group, (nViews + chunk - 1) / chunk * chunk);
-  DMI_CK(ctx->cls.ensure((size_t)group * npix * 4));
+  DMI_CK(ctx->cls.ensure(((size_t)group * npix + 1) * 4));   // + the spare slot holding -1.0f
   DMI_CK(ctx->tiles.ensure((size_t)group * tilesPerView * 4));
+  DMI_CK(ctx->viewscratch.ensure(sizeof(dmi::ViewFast) * dmi::kFastChunk));
   dmi::FastChunk* c = &ctx->fast_chunk;
   dmi::fill_fast_chunk_constants(g, c);
   for (int g0 = 0; g0 < nViews; g0 += group)
@@ -364,11 +365,13 @@ static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_dep
         if (!(k16[8] == 0.0 && k16[9] == 0.0 && k16[10] == 1.0 && k16[11] == 0.0)) c->pinhole = 0;
       }
       DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths + npix * (g0 + v0), (const float*)ctx->cls.p + npix * v0,
-                                   (const float*)ctx->tiles.p + tilesPerView * v0, ctx->opt_cull, ctx->vol.p,
+                                   (long long)(npix * (size_t)(gn - v0)),
+                                   (const float*)ctx->tiles.p + tilesPerView * v0, ctx->opt_cull,
+                                   (dmi::ViewFast*)ctx->viewscratch.p, ctx->vol.p,
                                    ctx->vol_type, ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr,
                                    ctx->stream));
       ctx->tsdf_stats.launches++;
-      ctx->total_launches++;
+      ctx->total_launches += 2;                           // the view-staging kernel and the integration kernel
     }
   }
   return DMI_OK;

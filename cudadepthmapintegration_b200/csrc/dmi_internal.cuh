@@ -78,11 +78,21 @@ struct FastCounters               // optional diagnostics (device memory, may be
 //                              the best-cost filter (never -1.0f on a valid pixel)
 //   tileDmax  float[n][TH][TW] per 16x16 tile of storage rows: max valid depth (rounded up), -inf when the
 //                              tile has no valid pixel, +inf when it holds a NaN
+// The tile statistics form a max-pyramid per view: level l has tiles of 16 * 2^l pixels, so that a brick
+// footprint of any size is covered by at most 2 x 2 tiles of the right level.
+struct TilePyramid
+{
+  int nLevels;
+  int perView;                    // floats per view, all levels
+  int tw[12], th[12], off[12];
+};
+TilePyramid tile_pyramid_layout(int W, int H);
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
                                  float* d_cls, float* d_tileDmax, cudaStream_t s);
+// d_cls[clsSpare] (an index relative to d_cls) must hold -1.0f: launch_prepare_views(n views) writes it at n*W*H
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
-                             const float* d_cls, const float* d_tileDmax, bool cull,
-                             void* d_vol, int scalarType, FastCounters* d_counters, cudaStream_t s);
+                             const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
+                             ViewFast* d_viewScratch, void* d_vol, int scalarType, FastCounters* d_counters, cudaStream_t s);
 void compose_fast_view(const GridParams& g, const double* K16, const double* RT16, int cxc, int cyc, ViewFast* out);
 void fill_fast_chunk_constants(const GridParams& g, FastChunk* c);
 

@@ -56,6 +56,40 @@ __device__ __forceinline__ float rcp_approx(float x)
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 
+// Phase C for one voxel: acc += ner when the voxel is valid, certainly farther than Delta from the depth
+// and in front of it; sets `bit` in `near` when it is valid but not certainly far.  Written in PTX so
+// that the add is PREDICATED (the compiler otherwise adds unconditionally and selects: 6 extra FSELs).
+__device__ __forceinline__ void classify_far(double& acc, unsigned& near, double ner, float fc, float d32, float thr, unsigned bit)
+{
+  asm("{\n\t"
+      ".reg .pred pv, pf, pa, pn;\n\t"
+      ".reg .f32 df, adf;\n\t"
+      "sub.rn.f32 df, %3, %4;\n\t"
+      "abs.f32 adf, df;\n\t"
+      "setp.neu.f32 pv, %4, 0fBF800000;\n\t"
+      "setp.gt.and.f32 pf, adf, %5, pv;\n\t"
+      "setp.lt.and.f32 pa, df, 0f00000000, pf;\n\t"
+      "@pa add.rn.f64 %0, %0, %2;\n\t"
+      "xor.pred pn, pv, pf;\n\t"
+      "@pn or.b32 %1, %1, %6;\n\t"
+      "}" : "+d"(acc), "+r"(near) : "d"(ner), "f"(fc), "f"(d32), "f"(thr), "r"(bit));
+}
+__device__ __forceinline__ void classify_far(float& acc, unsigned& near, float ner, float fc, float d32, float thr, unsigned bit)
+{
+  asm("{\n\t"
+      ".reg .pred pv, pf, pa, pn;\n\t"
+      ".reg .f32 df, adf;\n\t"
+      "sub.rn.f32 df, %3, %4;\n\t"
+      "abs.f32 adf, df;\n\t"
+      "setp.neu.f32 pv, %4, 0fBF800000;\n\t"
+      "setp.gt.and.f32 pf, adf, %5, pv;\n\t"
+      "setp.lt.and.f32 pa, df, 0f00000000, pf;\n\t"
+      "@pa add.rn.f32 %0, %0, %2;\n\t"
+      "xor.pred pn, pv, pf;\n\t"
+      "@pn or.b32 %1, %1, %6;\n\t"
+      "}" : "+f"(acc), "+r"(near) : "f"(ner), "f"(fc), "f"(d32), "f"(thr), "r"(bit));
+}
+
 __device__ __forceinline__ double affine(const double* r, double di, double dj, double dk)
 {
   return fma(di, r[0], fma(dj, r[1], fma(dk, r[2], r[3])));
@@ -122,7 +156,7 @@ __device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c,
 {
   outside = false;
   const float Eg = c.k3 * (fmaxf(fabsf(fbx) + 3.f * V.lx, fabsf(fby) + 3.f * V.ly) + c.umax1g * (fabsf(fbz) + 3.f * V.lz));
-  if (!(zlo > V.zm) || !(Eg * (1.0f / zlo) <= 0.25f)) return false;
+  if (!(zlo > V.zm) || !(Eg * rcp_approx(zlo) <= 0.24f)) return false;
   const float ei = (float)(FBI - 1), ej = (float)(FBJ - 1), ek = (float)(FM - 1);
   const float zi = V.fhz[0] * ei, zj = V.fhz[1] * ej, zk = V.fhz[2] * ek;
   const float xi = V.fnx[0] * ei, xj = V.fnx[1] * ej, xk = V.fnx[2] * ek;
@@ -132,7 +166,7 @@ __device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c,
   for (int q = 0; q < 8; q++)
   {
     const float hz = fbz + ((q & 1) ? zi : 0.f) + ((q & 2) ? zj : 0.f) + ((q & 4) ? zk : 0.f);
-    const float r = 1.0f / hz;
+    const float r = rcp_approx(hz);
     const float u = (fbx + ((q & 1) ? xi : 0.f) + ((q & 2) ? xj : 0.f) + ((q & 4) ? xk : 0.f)) * r;
     const float w = (fby + ((q & 1) ? yi : 0.f) + ((q & 2) ? yj : 0.f) + ((q & 4) ? yk : 0.f)) * r;
     umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
@@ -147,18 +181,36 @@ __device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c,
   if (!(xhi >= 0.f && xlo <= (float)(W - 1) && yhi >= 0.f && ylo <= (float)(H - 1))) { outside = true; return true; }
   const int px0 = max(0, (int)floorf(xlo)), px1 = min(W - 1, (int)ceilf(xhi));
   const int py0 = max(0, (int)floorf(ylo)), py1 = min(H - 1, (int)ceilf(yhi));
-  // storage rows are bottom-up: row = H-1-py
-  o.tx0 = px0 / kTile; o.tx1 = px1 / kTile; o.ty0 = (H - 1 - py1) / kTile; o.ty1 = (H - 1 - py0) / kTile;
+  // pixel bounds in STORAGE coordinates (rows are bottom-up: row = H-1-py)
+  o.tx0 = px0; o.tx1 = px1; o.ty0 = H - 1 - py1; o.ty1 = H - 1 - py0;
   o.valid = true;
   return true;
+}
+
+// Max of the valid depths over a pixel rectangle (storage coordinates), read from the pyramid level whose
+// tiles are at least as large as the rectangle: at most 2 x 2 tiles, all four loads in flight together.
+__device__ __forceinline__ float footprint_dmax(const TilePyramid& pyr, const float* __restrict__ td, const BrickBox& b)
+{
+  const int e = max(b.tx1 - b.tx0, b.ty1 - b.ty0);            // extent - 1
+  const int q = e >> 4;
+  const int L = min(q == 0 ? 0 : 32 - __clz(q), pyr.nLevels - 1);
+  const int sh = 4 + L;
+  const int tw = pyr.tw[L], th = pyr.th[L];
+  const int x0 = b.tx0 >> sh, x1 = min(b.tx1 >> sh, tw - 1), y0 = b.ty0 >> sh, y1 = min(b.ty1 >> sh, th - 1);
+  const float* t = td + pyr.off[L];
+  // beyond 2 x 2 only on the coarsest level, which is a single tile
+  const float a = __ldg(t + y0 * tw + x0), bq = __ldg(t + y0 * tw + x1);
+  const float cq = __ldg(t + y1 * tw + x0), dq = __ldg(t + y1 * tw + x1);
+  return fmaxf(fmaxf(a, bq), fmaxf(cq, dq));
 }
 
 template <typename T, bool PINHOLE, bool COUNT>
 __global__ void __launch_bounds__(FT)
 tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
                  const double* __restrict__ depths, const float* __restrict__ cls,
-                 const float* __restrict__ tileDmax, int cull, T* __restrict__ vol,
-                 int nbi, int nbj, int nbk, int TW, int TH, FastCounters* counters)
+                 const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
+                 long long clsSpare, const ViewFast* __restrict__ gviews, T* __restrict__ vol,
+                 int nbi, int nbj, int nbk, FastCounters* counters)
 {
   static_assert(kFastChunk <= FT, "one pre-pass thread per view");
   __shared__ ViewSm s_view[kFastChunk];
@@ -176,14 +228,18 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int W = g.W, H = g.H;
 
-  // ---- pre-pass: thread v prepares view v
+  // ---- pre-pass: the even threads prepare one view each (all four warps take part, so that none waits
+  // long at the barrier; lane order = view order, which the ballot compaction below preserves)
   {
-    const int v = threadIdx.x;
+    static_assert(2 * kFastChunk <= FT, "one even thread per view");
+    const int v = threadIdx.x >> 1;
     bool keep = false;
     float fbx = 0.f, fby = 0.f, fbz = 0.f, fbc = 0.f, Ux = c.umax1g, Uy = c.umax1g, czmaxabs = 0.f;
-    if (v < c.n)
+    // the pre-pass reads its view from the GLOBAL copy of the chunk: every lane wants a different view,
+    // which a constant-bank load would serialise 32 ways
+    const ViewFast& V = gviews[min(v, c.n - 1)];
+    if (!(threadIdx.x & 1) && v < c.n)
     {
-      const ViewFast& V = c.v[v];
       fbx = __double2float_rn(affine(V.nx, (double)i0, (double)j0, (double)k0));
       fby = __double2float_rn(affine(V.ny, (double)i0, (double)j0, (double)k0));
       fbz = __double2float_rn(affine(V.hz, (double)i0, (double)j0, (double)k0));
@@ -212,12 +268,9 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
       {
         if (zhi < -V.zm) keep = false;                        // the whole brick is behind the camera (:177)
         else if (boxed && outside) keep = false;              // ... projects outside the image (:192-197)
-        else if (boxed && box.valid && (box.tx1 - box.tx0 + 1) * (box.ty1 - box.ty0 + 1) <= 64)
+        else if (boxed && box.valid)
         {
-          const float* td = tileDmax + (size_t)v * TW * TH;
-          float dmax = -INFINITY;
-          for (int ty = box.ty0; ty <= box.ty1; ty++)
-            for (int tx = box.tx0; tx <= box.tx1; tx++) dmax = fmaxf(dmax, __ldg(td + ty * TW + tx));
+          const float dmax = footprint_dmax(pyr, tileDmax + (size_t)v * pyr.perView, box);
           const float thr = c.delta_up + 1e-6f * czmaxabs;
           // no valid pixel under the brick (:202), or every voxel farther than Delta BEHIND every valid
           // depth it can meet: rayPotential returns 0 (:114-115)
@@ -232,7 +285,6 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
     {
       int pos = __popc(bal & ((1u << lane) - 1u));
       for (int q = 0; q < w; q++) pos += s_cnt[q];
-      const ViewFast& V = c.v[v];
       ViewSm& S = s_view[pos];
       const float Ex = c.k3 * ((fabsf(fbx) + 3.f * V.lx) + Ux * (fabsf(fbz) + 3.f * V.lz));
       const float Ey = c.k3 * ((fabsf(fby) + 3.f * V.ly) + Uy * (fabsf(fbz) + 3.f * V.lz));
@@ -274,6 +326,7 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
 
   const size_t npix = (size_t)W * H;
   const int pxoff = kMagicBits - c.cxc, pyoff = kMagicBits - c.cyc;
+  const int negW = -W;
   const double delta = g.delta, thick = g.thick;
   const T nerT = (T)g.neg_eta_rho;
   unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0;
@@ -296,6 +349,9 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
     const float* cv = cls + voff;
     const double* dv = depths + voff;
     asm volatile("" : "+l"(cv), "+l"(dv));                    // keep them as plain 64-bit registers
+    // rejected voxels gather the spare float behind the classification images, which holds -1.0f:
+    // no predicate, no default value, one sector for the whole warp
+    const int rej = (int)(clsSpare - (long long)voff);
 
     // ---- phase A: classify all FM voxels with the FP32 tier
     int idx[FM];
@@ -316,7 +372,7 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
       const int px = __float_as_int(tu) - pxoff;
       const int py = __float_as_int(tv) - pyoff;
       const bool ok = cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H;
-      idx[m] = ok ? px - py * W : kReject;
+      idx[m] = ok ? px + py * negW : rej;
       anyv |= ok;
       if (!cert) need |= 1u << m;
       if (COUNT) n_t1 += cert ? 1 : 0;
@@ -333,17 +389,20 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
         const float fm = (float)m;
         const float fz = fmaf(fm, kz, fhz0);
         int id = kReject;                                                    // certified behind the camera
+        bool okm = false;
         if (!(fz < -zm))
         {
           if (COUNT) n_t2++;
           const float r = rcp_approx(fz);
           const float pu = fmaf(fmaf(fm, kx, fnx0), r, kMagic) - kMagic, pv = fmaf(fmaf(fm, ky, fny0), r, kMagic) - kMagic;
           id = tier2(c.v[v], c.cxc, c.cyc, W, H, di, dj, dk0 + (double)m, pu, pv);
-          if (id == kNeedExact) { need3 |= 1u << m; id = kReject; }
+          if (id == kNeedExact) need3 |= 1u << m;
+          okm = id > kBad;
         }
+        if (!okm) id = rej;
 #pragma unroll
         for (int mm = 0; mm < FM; mm++) if (mm == m) idx[mm] = id;
-        anyv |= id > kBad;
+        anyv |= okm;
       }
       if (need3)
       {
@@ -361,25 +420,26 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
     // ---- phase B: all gathers of the float classification image in flight together
     float d32[FM];
 #pragma unroll
-    for (int m = 0; m < FM; m++) d32[m] = (idx[m] > kBad) ? __ldg(cv + idx[m]) : -1.0f;
+    for (int m = 0; m < FM; m++) d32[m] = __ldg(cv + idx[m]);
 
-    // ---- phase C: FP32 classification; -1.0f = invalid after the filter (:202)
+    // ---- phase C: FP32 classification; -1.0f = invalid after the filter (:202).  In front and farther
+    // than Delta (certified by the margin in thrfar): -Eta*Rho; behind and farther: 0 (:114-115);
+    // everything else that is valid (NaN included) goes to the FP64 band below.
     unsigned near = 0;
 #pragma unroll
     for (int m = 0; m < FM; m++)
     {
       const float fc = PINHOLE ? fmaf((float)m, kz, fhz0) : fmaf((float)m, kc, fcz0);   // camera z (:207)
-      const float df = fc - d32[m];
-      const bool valid = d32[m] != -1.0f;
-      const bool far = fabsf(df) > thrfar;                                   // certainly |diff| > Delta (:114)
-      if (valid && far && df < 0.f) acc[m] += nerT;                          // in front: -Eta*Rho; behind: 0 (:115)
-      if (valid && !far) near |= 1u << m;                                    // NaN lands here too
+      classify_far(acc[m], near, nerT, fc, d32[m], thrfar, 1u << m);
     }
     // ---- the band around the surface: double depth, FP64 potential
     if (near)
     {
       const double zij = __fma_rn(di, S.czr[0], __fma_rn(dj, S.czr[1], S.czr[3]));
       const double czk = S.czr[2], gd = S.gd;
+      double dd[FM];
+#pragma unroll
+      for (int m = 0; m < FM; m++) dd[m] = (near & (1u << m)) ? __ldg(dv + idx[m]) : 0.0;
 #pragma unroll
       for (int m = 0; m < FM; m++)
       {
@@ -388,9 +448,8 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
           if (COUNT) n_nb++;
           // explicit roundings: the value of a voxel must not depend on which unrolled copy (m) or
           // brick decomposition evaluates it, so that z-slabs concatenate bit-identically
-          const double d = __ldg(dv + idx[m]);
           const double z = __fma_rn(dk0 + (double)m, czk, zij);              // :207, from GLOBAL indices
-          const double diff = __dsub_rn(z, d);
+          const double diff = __dsub_rn(z, dd[m]);
           const double ad = fabs(diff);
           const double td = __dsub_rn(ad, delta);
           if (fabs(td) < gd)
@@ -400,7 +459,7 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
           }
           else if (td > 0.0)
           {
-            if (!(diff > 0.0)) acc[m] += nerT;                               // :114-115
+            if (!(diff > 0.0)) acc[m] = add_rn(acc[m], nerT);                // :114-115
           }
           else
           {
@@ -427,46 +486,77 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   }
 }
 
+__global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant__ FastChunk c, ViewFast* __restrict__ dst)
+{
+  const unsigned* src = reinterpret_cast<const unsigned*>(c.v);
+  unsigned* d = reinterpret_cast<unsigned*>(dst);
+  const int words = (int)(sizeof(ViewFast) / 4) * c.n;
+  for (int q = threadIdx.x; q < words; q += blockDim.x) d[q] = src[q];
+}
+
 template <typename T, bool PINHOLE>
 static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths,
-                           const float* d_cls, const float* d_tileDmax, bool cull, T* d_vol, int nbi, int nbj,
-                           int nbk, int TW, int TH, FastCounters* d_counters, cudaStream_t s)
+                           const float* d_cls, const float* d_tileDmax, const TilePyramid& pyr, bool cull,
+                           long long clsSpare, const ViewFast* d_views, T* d_vol, int nbi, int nbj, int nbk,
+                           FastCounters* d_counters, cudaStream_t s)
 {
   if (d_counters)
-    tsdf_fast_kernel<T, PINHOLE, true><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, cull ? 1 : 0, d_vol, nbi, nbj, nbk, TW, TH, d_counters);
+    tsdf_fast_kernel<T, PINHOLE, true><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, d_vol, nbi, nbj, nbk, d_counters);
   else
-    tsdf_fast_kernel<T, PINHOLE, false><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, cull ? 1 : 0, d_vol, nbi, nbj, nbk, TW, TH, nullptr);
+    tsdf_fast_kernel<T, PINHOLE, false><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, d_vol, nbi, nbj, nbk, nullptr);
 }
 
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
-                             const float* d_cls, const float* d_tileDmax, bool cull,
-                             void* d_vol, int scalarType, FastCounters* d_counters, cudaStream_t s)
+                             const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
+                             ViewFast* d_viewScratch, void* d_vol, int scalarType, FastCounters* d_counters, cudaStream_t s)
 {
   const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
   if (nbi <= 0 || nbj <= 0 || nbk <= 0 || c.n <= 0) return cudaSuccess;
   const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
   const unsigned grid = nsi * nsj * nsk * (FSI * FSJ * FSK);
-  const int TW = (g.W + kTile - 1) / kTile, TH = (g.H + kTile - 1) / kTile;
+  const TilePyramid pyr = tile_pyramid_layout(g.W, g.H);
+  // stream-ordered copy of the views from the parameter space to global memory, for the pre-pass
+  stage_views_kernel<<<1, 256, 0, s>>>(c, d_viewScratch);
+  const ViewFast* d_views = d_viewScratch;
   if (scalarType == 1)
   {
-    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (double*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
-    else launch_variant<double, false>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (double*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
+    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
+    else launch_variant<double, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
   }
   else
   {
-    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (float*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
-    else launch_variant<float, false>(grid, g, c, d_depths, d_cls, d_tileDmax, cull, (float*)d_vol, nbi, nbj, nbk, TW, TH, d_counters, s);
+    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
+    else launch_variant<float, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
   }
   return cudaGetLastError();
 }
 
 // ---- view preparation: best-cost filter (ReconstructionData.cxx:159-166) folded into a float
-// classification image, plus per-tile statistics for the brick culling.  One warp per 16x16 tile of
-// storage rows, each lane 8 consecutive pixels; a single HBM-bound pass over the maps.
+// classification image, plus the tile max-pyramid for the brick culling.  Level 0: one warp per 16x16
+// tile of storage rows, each lane 8 consecutive pixels; a single HBM-bound pass over the maps.
+TilePyramid tile_pyramid_layout(int W, int H)
+{
+  TilePyramid p;
+  int tw = (W + kTile - 1) / kTile, th = (H + kTile - 1) / kTile, off = 0, l = 0;
+  for (;; l++)
+  {
+    p.tw[l] = tw; p.th[l] = th; p.off[l] = off;
+    off += tw * th;
+    if ((tw == 1 && th == 1) || l == 11) break;
+    tw = (tw + 1) / 2; th = (th + 1) / 2;
+  }
+  p.nLevels = l + 1;
+  for (int q = p.nLevels; q < 12; q++) { p.tw[q] = 1; p.th[q] = 1; p.off[q] = p.off[p.nLevels - 1]; }
+  p.perView = off;
+  return p;
+}
+
 __global__ void __launch_bounds__(256)
 prepare_views_kernel(const double* __restrict__ depths, const double* __restrict__ cost, double thr,
-                     int nViews, int W, int H, int TW, int TH, float* __restrict__ cls, float* __restrict__ tileDmax)
+                     int nViews, int W, int H, int TW, int TH, int perView, float* __restrict__ cls,
+                     float* __restrict__ tileDmax)
 {
+  if (blockIdx.x == 0 && threadIdx.x == 0) cls[(size_t)nViews * W * H] = -1.0f;   // the spare slot, see phase B
   const int lane = threadIdx.x & 31;
   const size_t tile = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t tilesPerView = (size_t)TW * TH;
@@ -502,17 +592,39 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-  if (lane == 0) tileDmax[tile] = dmax;
+  if (lane == 0) tileDmax[(size_t)v * perView + t] = dmax;
+}
+
+// level l from level l-1: max over the (up to) 2 x 2 children
+__global__ void __launch_bounds__(256)
+tile_pyramid_kernel(float* __restrict__ tiles, int nViews, int perView, int offSrc, int twS, int thS,
+                    int offDst, int twD, int thD)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)twD * thD;
+  if (t >= per * nViews) return;
+  const int v = (int)(t / per), q = (int)(t % per);
+  const int y = q / twD, x = q % twD;
+  const float* src = tiles + (size_t)v * perView + offSrc;
+  const int x0 = 2 * x, x1 = min(2 * x + 1, twS - 1), y0 = 2 * y, y1 = min(2 * y + 1, thS - 1);
+  const float m = fmaxf(fmaxf(src[y0 * twS + x0], src[y0 * twS + x1]), fmaxf(src[y1 * twS + x0], src[y1 * twS + x1]));
+  tiles[(size_t)v * perView + offDst + q] = m;
 }
 
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
                                  float* d_cls, float* d_tileDmax, cudaStream_t s)
 {
-  const int TW = (W + kTile - 1) / kTile, TH = (H + kTile - 1) / kTile;
-  const size_t tiles = (size_t)TW * TH * nViews;
+  const TilePyramid p = tile_pyramid_layout(W, H);
+  const size_t tiles = (size_t)p.tw[0] * p.th[0] * nViews;
   if (tiles == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((tiles + 7) / 8);
-  prepare_views_kernel<<<blocks, 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, TW, TH, d_cls, d_tileDmax);
+  prepare_views_kernel<<<blocks, 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw[0], p.th[0], p.perView, d_cls, d_tileDmax);
+  for (int l = 1; l < p.nLevels; l++)
+  {
+    const size_t n = (size_t)p.tw[l] * p.th[l] * nViews;
+    tile_pyramid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_tileDmax, nViews, p.perView, p.off[l - 1], p.tw[l - 1],
+                                                                  p.th[l - 1], p.off[l], p.tw[l], p.th[l]);
+  }
   return cudaGetLastError();
 }
 
