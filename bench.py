@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the depth-map integration hot path (BASELINE.json: voxel*view updates/sec,
-1024^3 cells x 1000 views 1920x1080, z-slab sharded over 1/2/4/8 B200).
+1024^3 cells x 1000 views 1920x1080, z-slab sharded over 1/2/4/8 B200; colored points/sec).
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
     python bench.py --impl reference ...                     (the reference's own kernel text on host cores)
 
 One "step" = one full integration of all views into a zeroed volume.  Rank 0 prints ONE JSON line.
   value   device-resident: every rank's share of the views already sits in its HBM; the timed region
-          covers best-cost filtering, the NCCL view all-gather (N>1), all integration launches and
-          the slab gather to rank 0 (N>1).  CUDA events, barrier + synchronize both sides, max over ranks.
-  e2e     the same job through the host-pointer C-ABI call (dmi_process_depth_maps at N=1): pinned
-          host views -> H2D -> filter -> integrate -> D2H of the volume, all inside the timed region.
+          covers view preparation (best-cost filter), the NCCL view all-gather (N>1), all integration
+          launches and the slab gather to rank 0 (N>1).  CUDA events, barrier + synchronize both sides,
+          max over ranks.
+  e2e     the same job from pinned HOST buffers: H2D of the views (and of io_scalar at N=1, which the
+          reference's call also uploads), the job, D2H of the volume, all inside the timed region.
+          N=1 goes through dmi_process_depth_maps, the drop-in for ProcessDepthMap<double>.
 Synthetic data: unit sphere, Fibonacci-sphere pinhole cameras, generated on the GPU.
 """
 from __future__ import annotations
@@ -29,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 THRESH = 0.14            # --threshBestCost default, Reconstruction/main.cxx:79
 FLOPS_PER_UNIT = 28.0    # algorithmic flops per voxel*view (FMA = 2)
+COLOR_FLOPS_PER_UNIT = 37.0
 
 WORKLOADS = {
     # name: (cells per axis, views, W, H)
@@ -49,9 +52,11 @@ def parse_args():
     ap.add_argument("--kernel", default="auto", choices=["auto", "exact"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-coloration", action="store_true")
     ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
-    ap.add_argument("--counters", action="store_true", help="print the fast kernel's tier counters to stderr (slower kernel build)")
-    ap.add_argument("--group", type=int, default=40, help="views per all-gather group (N>1)")
+    ap.add_argument("--group", type=int, default=128, help="views per all-gather group (N>1)")
+    ap.add_argument("--color-points", type=int, default=2000000)
+    ap.add_argument("--color-views", type=int, default=200)
     return ap.parse_args()
 
 
@@ -74,7 +79,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -116,8 +121,7 @@ class ClockSampler:
 def cpu_reference_rate(N, V, W, H, target_seconds=12.0, steps=1, warmup=0):
     """Times oracle/_ref/libref_tsdf_host.so (kind "reference") or, if absent, oracle/liboracle.so
     (kind "port") on a bounded sample of the workload: all N x N cells of `nz` z-planes in the middle
-    of the grid x `nv` views.  Returns (units/s, description dict)."""
-    import torch
+    of the grid x `nv` views.  Returns (units/s, description dict, seconds per step)."""
     from cudadepthmapintegration_b200 import synthetic as syn
     from tests import _oracle
     ref = _oracle.load_ref_host()
@@ -170,12 +174,76 @@ def run_reference(args):
         "impl": "reference", "metric": "voxel*view updates/sec", "value": rate, "unit": "voxel*views/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H} (bounded sample per step, see cpu_baseline.sample)"},
+        "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H} (bounded sample per step, see cpu_baseline.sample)",
+                   "name": args.workload},
         "cpu_baseline": dict(desc, value=rate, unit="voxel*views/s"),
         "e2e": {"value": rate, "unit": "voxel*views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# coloration (secondary metric: colored points/sec)
+# ------------------------------------------------------------------------------------------------
+
+def mesh_points(P):
+    """Stand-in for the isocontour's vertices (VTK is not installed): P points on the unit sphere in
+    scanline order (sorted by z, then y, then x cell like a marching-cubes traversal), float32."""
+    from cudadepthmapintegration_b200 import synthetic as syn
+    pts = syn.fibonacci_sphere_points(P).astype(np.float64)
+    cell = np.floor((pts + 1.2) / (2.4 / 1024)).astype(np.int64)
+    order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
+    return np.ascontiguousarray(pts[order].astype(np.float32))
+
+
+def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
+    from cudadepthmapintegration_b200 import synthetic as syn
+    from tests import _oracle
+    P, V = args.color_points, args.color_views
+    K, RT = syn.make_cameras(V, W, H)
+    cols = torch.empty((V, H, W, 3), dtype=torch.uint8, device=dev)
+    for v0 in range(0, V, 8):
+        _, _, c = syn.render_views(K[v0:v0 + 8], RT[v0:v0 + 8], W, H, first_view=v0, device=dev, want_best_cost=False)
+        cols[v0:v0 + 8] = c
+    pts_h = mesh_points(P)
+    pts = torch.from_numpy(pts_h).to(dev)
+    mean = torch.zeros((P, 3), dtype=torch.uint8, device=dev)
+    med = torch.zeros_like(mean)
+    nb = torch.zeros(P, dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.colorize_device(P, pts.data_ptr(), np.float32, V, cols.data_ptr(), K, RT, W, H, mean.data_ptr(), med.data_ptr(), nb.data_ptr())
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ctx.color_kernel_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    kms, kn = ctx.color_kernel_stats()
+    out = {"metric": "colored points/sec", "value": P / (ms * 1e-3), "unit": "points/s", "point_views_per_s": P * V / (ms * 1e-3),
+           "ms_per_step": ms, "kernel_ms_per_step": kms / max(kn, 1),
+           "config": {"workload": f"mesh coloration {P} points (sphere, scanline order, float32) x {V} views {W}x{H}"},
+           "gpu_launches_per_step": kn / max(steps, 1)}
+    # parity spot check + CPU baseline on a bounded sample (the oracle, OpenMP over points)
+    orc = _oracle.load_oracle()
+    ns = min(P, 20000)
+    cols_h = cols.cpu().numpy()
+    t0 = time.perf_counter()
+    wmean, wmed, wnb = orc.colorize(pts_h[:ns], cols_h, K, RT, W, H)
+    dt = time.perf_counter() - t0
+    ok = (np.array_equal(nb[:ns].cpu().numpy(), wnb) and np.array_equal(med[:ns].cpu().numpy(), wmed)
+          and np.array_equal(mean[:ns].cpu().numpy(), wmean))
+    out["parity_sample_ok"] = bool(ok)
+    out["cpu_baseline"] = {"value": ns / dt, "unit": "points/s", "cores": os.cpu_count() or 1, "kind": "port",
+                           "sample": f"first {ns} points x {V} views, oracle/color_oracle.c, OpenMP over points, {dt * 1e3:.0f} ms"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,13 +276,12 @@ def main():
     rp = syn.make_ray_potential(grid)
     K, RT = syn.make_cameras(V, W, H)
     k0, k1 = sharding.slab_range(N, rank, world)
+    slab_cells = (k1 - k0) * N * N
 
     ctx = Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_EXACT if args.kernel == "exact" else _lib.DMI_TSDF_KERNEL_AUTO)
     ctx.set_option(_lib.DMI_OPT_CULL, args.cull)
-    if args.counters:
-        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 1)
     ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
     ctx.set_slab(k0, k1)
 
@@ -224,10 +291,9 @@ def main():
     G = max(world, (G // world) * world)
     groups = [(g0, min(V, g0 + G)) for g0 in range(0, V, G)]
 
-    def owned(g0, g1):
-        n = g1 - g0
-        per = (n + world - 1) // world
-        a = min(g1, g0 + rank * per)
+    def owned(g0, g1, r=rank):
+        per = (g1 - g0 + world - 1) // world
+        a = min(g1, g0 + r * per)
         return a, min(g1, a + per), per
 
     # ---- generate this rank's views on its GPU (stands for "loaded from the files it owns")
@@ -243,8 +309,7 @@ def main():
     my_cost = torch.empty((nmine, H, W), dtype=torch.float64, device=dev)
     for s0 in range(0, nmine, 8):
         idx = my_idx[s0:s0 + 8]
-        # consecutive runs only (render_views hashes on first_view + offset)
-        runs = np.split(idx, np.where(np.diff(idx) != 1)[0] + 1)
+        runs = np.split(idx, np.where(np.diff(idx) != 1)[0] + 1)     # render_views hashes on first_view + offset
         off = s0
         for r in runs:
             d, c, _ = syn.render_views(K[r], RT[r], W, H, first_view=int(r[0]), device=dev, depth_noise=noise, want_color=False)
@@ -256,12 +321,14 @@ def main():
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
 
-    def _as_tensor(ptr, count):
-        """Wrap the context's slab (device memory owned by libdmi_b200) as a tensor, without copying."""
+    def slab_tensor():
+        """The context's slab (device memory owned by libdmi_b200) as a tensor, without copying."""
+        ptr, _ = ctx.volume_device_ptr()
+
         class _Holder:
             pass
         h = _Holder()
-        h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        h.__cuda_array_interface__ = {"shape": (slab_cells,), "typestr": "<f8", "data": (ptr, False), "version": 3}
         return torch.as_tensor(h, device=dev)
 
     def step_device():
@@ -274,7 +341,7 @@ def main():
         comm_stream.wait_stream(cur)
         events = []
         off = 0
-        # filter own views into place, all-gather group by group on the comm stream
+        # filter own views into place, all-gather group by group on the comm stream, integrate behind it
         with torch.cuda.stream(comm_stream):
             for (g0, g1) in groups:
                 a, b, per = owned(g0, g1)
@@ -289,7 +356,7 @@ def main():
                     dist.all_gather_into_tensor(all_depths[g0:g1].view(-1), all_depths[a:b].view(-1))
                 else:   # ragged last group: plain broadcasts from each owner
                     for r in range(world):
-                        ra = min(g1, g0 + r * per); rb = min(g1, ra + per)
+                        ra, rb, _ = owned(g0, g1, r)
                         if rb > ra:
                             dist.broadcast(all_depths[ra:rb], src=r)
                 ev = torch.cuda.Event()
@@ -298,10 +365,8 @@ def main():
         for (g0, g1), ev in zip(groups, events):
             cur.wait_event(ev)
             ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
-        # the finished slabs are gathered once (for contouring on rank 0)
-        ptr, nbytes = ctx.volume_device_ptr()
-        slab = _as_tensor(ptr, (k1 - k0) * N * N)
-        # slabs may differ by one plane: gather with explicit point-to-point transfers
+        # the finished slabs are gathered once (for contouring on rank 0); slabs may differ by one plane
+        slab = slab_tensor()
         if rank == 0:
             full_volume[k0 * N * N:k1 * N * N].copy_(slab)
             reqs = []
@@ -318,20 +383,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+    def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps
+        return float(ms[0].item()) / steps, float(ms[1].item()) / steps
 
     units = float(N) ** 3 * V
 
@@ -341,8 +406,6 @@ def main():
 
     # ---- device-resident timing
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ctx.tsdf_kernel_stats()
-    launches0 = ctx.launch_counter()
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -350,18 +413,30 @@ def main():
     launches0 = ctx.launch_counter()
     if sampler:
         sampler.start()
-    ms_step = timed(step_device, args.steps, 0)
+    ms_step, _ = timed(step_device, args.steps)
     clocks = sampler.stop() if sampler else None
     kernel_ms, kernel_launches = ctx.tsdf_kernel_stats()
     launches = ctx.launch_counter() - launches0
-    if args.counters and args.kernel != "exact":
-        print("tier counters (rank %d): %s" % (rank, ctx.tsdf_tier_counters()), file=sys.stderr)
     value = units / (ms_step * 1e-3)
 
-    # ---- end to end through the host-pointer ABI
+    # ---- how much of the work the fast kernel actually evaluated (diagnostic build of the kernel, untimed)
+    tiers = None
+    if args.kernel != "exact":
+        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 1)
+        step_device()
+        barrier()
+        tiers = ctx.tsdf_tier_counters()
+        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 0)
+
+    # ---- end to end from host buffers
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(args, ctx, torch, dist, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, my_idx, k0, k1, units, barrier)
+        e2e = measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units,
+                          step_device, slab_tensor, timed)
+
+    coloration = None
+    if rank == 0 and world == 1 and not args.no_coloration:
+        coloration = measure_coloration(args, ctx, torch, dev, W, H, max(1, args.steps), max(1, args.warmup))
 
     if rank == 0:
         peaks = {}
@@ -372,22 +447,36 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         # dominant kernel = the integration kernel; per launch: algorithmic flops / bytes over its mean duration
-        k_units = units * args.steps / world                         # this rank's units over the timed region
+        k_units = units * args.steps / world                         # this rank's pairs over the timed region
         k_sec = kernel_ms * 1e-3
-        ach_tflops = FLOPS_PER_UNIT * k_units / k_sec / 1e12
+        all_pairs_tflops = FLOPS_PER_UNIT * k_units / k_sec / 1e12
+        evaluated = 1.0
+        if tiers and tiers["brick_views"] > 0:
+            evaluated = 1.0 - tiers["culled_brick_views"] / tiers["brick_views"]
+        ach = all_pairs_tflops * evaluated
         alg_bytes = algorithmic_bytes(N, V, W, H) / world * args.steps
         roofline = {
-            "bound": "fp64", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tflops / fp64_peak,
+            "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
             "traffic": None,
-            "kernel": "tsdf integration kernel (all launches of the timed region, CUDA events on the launch stream)",
-            "peak_source": "DFMA issue-rate microbenchmark run in this process (dmi_measure_fp_peak); MEASURED_PEAKS.json has no FP64 vector peak",
+            "kernel": "tsdf_fast_kernel" if args.kernel != "exact" else "tsdf_exact_kernel",
+            "definition": "28 algorithmic flops x the voxel*view pairs the kernel EVALUATED (pairs culled by the exact brick tests "
+                          "are excluded) / summed CUDA-event time of the integration launches of the timed region",
+            "peak_source": "FFMA issue-rate microbenchmark run in this process (dmi_measure_fp_peak); MEASURED_PEAKS.json has no FP32/FP64 vector peak",
+            "binding_resource": "instruction issue (compares, rounding, address arithmetic, one gather per pair): see profiles/ for smsp__issue_active",
+            "evaluated_fraction_of_pairs": evaluated,
+            "all_pairs": {"achieved": all_pairs_tflops, "frac_fp32": all_pairs_tflops / fp32_peak, "frac_fp64": all_pairs_tflops / fp64_peak,
+                          "note": "all N^3*V pairs counted as SURVEY.md 8d asks; exceeds the FMA roofline because most pairs are proven to contribute nothing without being evaluated"},
+            "fp64_basis": {"peak": fp64_peak, "frac": ach / fp64_peak, "peak_source": "DFMA microbenchmark, this process"},
             "algorithmic_flops_per_unit": FLOPS_PER_UNIT,
             "kernel_ms_per_step": kernel_ms / args.steps, "kernel_launches_per_step": kernel_launches / args.steps,
-            "fp32_basis": {"peak": fp32_peak, "frac": ach_tflops / fp32_peak, "peak_source": "FFMA microbenchmark, this process"},
-            "hbm": {"achieved": alg_bytes / k_sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": alg_bytes / k_sec / 1e9 / hbm_peak, "peak_source": hbm_src,
-                    "note": "algorithmic bytes (volume once in/out + every depth and best-cost map once) over kernel time; not the binding roofline"},
+            "hbm": {"achieved": alg_bytes / k_sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / k_sec / 1e9 / hbm_peak,
+                    "peak_source": hbm_src, "note": "algorithmic bytes (volume once in/out + every depth and best-cost map once) over kernel time; not the binding roofline"},
         }
+        if tiers:
+            u = max(tiers["units"], 1)
+            roofline["tiers"] = {"fp32_certified": tiers["t1_certified"] / u, "fp64_tier": tiers["t2_entered"] / u,
+                                 "exact_tier": tiers["t3_entered"] / u, "band_fp64": tiers["near_band"] / u,
+                                 "note": "fractions of the evaluated pairs (rank 0)"}
         line = {
             "metric": "voxel*view updates/sec", "value": value, "unit": "voxel*views/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -395,11 +484,13 @@ def main():
             "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H}, best-cost threshold {THRESH}, f64 volume",
                        "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views all-gathered in groups of {G}" if world > 1 else ""),
                        "l2": "inputs (%.1f GB per step) exceed L2; no flush needed" % (algorithmic_bytes(N, V, W, H) / 1e9),
-                       "kernel": args.kernel},
+                       "kernel": args.kernel, "cull": args.cull},
             "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if coloration is not None:
+            line["coloration"] = coloration
         if not args.no_cpu_baseline and world == 1:
             rate, desc, _ = cpu_reference_rate(N, V, W, H, target_seconds=12.0)
             line["cpu_baseline"] = dict(desc, value=rate, unit="voxel*views/s")
@@ -410,49 +501,44 @@ def main():
     ctx.close()
 
 
-def measure_e2e(args, ctx, torch, dist, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, my_idx, k0, k1, units, barrier):
-    """Host buffers in, host volume out, through dmi_process_depth_maps (N=1) or the streaming ABI (N>1)."""
+def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units,
+                step_device, slab_tensor, timed):
+    """Host buffers in, host volume out."""
     import psutil
     npix = W * H
     nmine = my_depths.shape[0]
-    slab_cells = (k1 - k0) * N * N
     need = 2 * nmine * npix * 8 + slab_cells * 8
     avail = psutil.virtual_memory().available
-    if need > 0.6 * avail:
-        return {"value": None, "unit": "voxel*views/s", "skipped": f"host buffers need {need / 1e9:.0f} GB, {avail / 1e9:.0f} GB available"}
+    if need * world > 0.7 * avail:
+        return {"value": None, "unit": "voxel*views/s", "skipped": f"host buffers need {need * world / 1e9:.0f} GB, {avail / 1e9:.0f} GB available"}
     h_depths = torch.empty((nmine, H, W), dtype=torch.float64, pin_memory=True)
     h_cost = torch.empty((nmine, H, W), dtype=torch.float64, pin_memory=True)
     h_vol = torch.zeros(slab_cells, dtype=torch.float64, pin_memory=True)
     h_depths.copy_(my_depths)
     h_cost.copy_(my_cost)
     torch.cuda.synchronize()
-    if world > 1:
-        # multi-GPU e2e is reported by the device-resident number plus each rank's own H2D/D2H; keep it simple:
-        # every rank uploads its views, the job runs as in step_device, every rank downloads its slab.
-        return {"value": None, "unit": "voxel*views/s", "skipped": "e2e is measured at N=1 in this round"}
-    vol_np = h_vol.numpy()
-    d_np, c_np = h_depths.numpy(), h_cost.numpy()
-
-    def step():
-        vol_np.fill(0.0)          # the filter zero-fills its output before the call (vtkCudaReconstructionFilter.cxx:133)
-        ctx.process_depth_maps(d_np, c_np, THRESH, K, RT, vol_np)
-
     steps = max(1, min(args.steps, 2))
+    if world == 1:
+        vol_np, d_np, c_np = h_vol.numpy(), h_depths.numpy(), h_cost.numpy()
+
+        def step():
+            vol_np.fill(0.0)      # the filter zero-fills its output before the call (vtkCudaReconstructionFilter.cxx:133)
+            ctx.process_depth_maps(d_np, c_np, THRESH, K, RT, vol_np)
+        api = "dmi_process_depth_maps (host pointers; pinned host buffers; includes the upload of io_scalar the reference also does)"
+        h2d = int(2 * nmine * npix * 8 + slab_cells * 8)
+    else:
+        def step():
+            my_depths.copy_(h_depths, non_blocking=True)
+            my_cost.copy_(h_cost, non_blocking=True)
+            step_device()
+            h_vol.copy_(slab_tensor(), non_blocking=True)
+        api = "per rank: H2D of its share of the views, dmi_volume_integrate_device after the NCCL all-gather, D2H of its slab"
+        h2d = int(2 * nmine * npix * 8)
     step()
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    barrier()
-    wall = (time.perf_counter() - t0) / steps
-    ms = e0.elapsed_time(e1) / steps
-    sec = max(wall, ms * 1e-3)
+    ms, wall = timed(step, steps)
+    sec = max(ms, wall) * 1e-3
     return {"value": units / sec, "unit": "voxel*views/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": 1,
-            "h2d_bytes_per_step": int(2 * nmine * npix * 8 + slab_cells * 8), "d2h_bytes_per_step": int(slab_cells * 8),
-            "api": "dmi_process_depth_maps (host pointers; pinned host buffers; includes the upload of io_scalar the reference also does)"}
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(slab_cells * 8), "bytes_are": "per rank", "api": api}
 
 
 if __name__ == "__main__":
