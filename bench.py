@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-coloration", action="store_true")
     ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
     ap.add_argument("--group", type=int, default=128, help="views per all-gather group (N>1)")
+    ap.add_argument("--breakdown", action="store_true", help="N>1: print the comm / compute / gather spans of the last step to stderr")
     ap.add_argument("--color-points", type=int, default=2000000)
     ap.add_argument("--color-views", type=int, default=200)
     return ap.parse_args()
@@ -258,7 +259,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cudadepthmapintegration_b200 import Context, _lib, sharding, synthetic as syn
+    from cudadepthmapintegration_b200 import Context, _lib, sharding, synthetic as syn, distributed as D
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,23 +288,16 @@ def main():
 
     # ---- view ownership: groups of G views; inside a group rank r owns a contiguous G/world share, so
     # that an in-place all-gather of the group's region of the resident buffer assembles it.
-    G = args.group if world > 1 else V
-    G = max(world, (G // world) * world)
-    groups = [(g0, min(V, g0 + G)) for g0 in range(0, V, G)]
+    groups = D.view_groups(V, args.group if world > 1 else V, world)
+    G = groups[0][1] - groups[0][0]
 
     def owned(g0, g1, r=rank):
-        per = (g1 - g0 + world - 1) // world
-        a = min(g1, g0 + r * per)
-        return a, min(g1, a + per), per
+        return D.owned_range(g0, g1, r, world)
 
     # ---- generate this rank's views on its GPU (stands for "loaded from the files it owns")
     noise = 0.25 * float(grid.spacing.max())
     all_depths = torch.empty((V, H, W), dtype=torch.float64, device=dev) if world > 1 else None
-    my_idx = []
-    for (g0, g1) in groups:
-        a, b, _ = owned(g0, g1)
-        my_idx.extend(range(a, b))
-    my_idx = np.array(my_idx, dtype=np.int64)
+    my_idx = np.array(D.owned_views(V, args.group if world > 1 else V, rank, world), dtype=np.int64)
     nmine = len(my_idx)
     my_depths = torch.empty((nmine, H, W), dtype=torch.float64, device=dev)
     my_cost = torch.empty((nmine, H, W), dtype=torch.float64, device=dev)
@@ -318,7 +312,9 @@ def main():
             off += len(r)
     torch.cuda.synchronize()
 
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    # high priority: the all-gather's few CTAs must not queue behind a million integration CTAs
+    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    marks = {}
     full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
 
     def slab_tensor():
@@ -339,6 +335,10 @@ def main():
             return
         cur = torch.cuda.current_stream()
         comm_stream.wait_stream(cur)
+        if args.breakdown:
+            for nm in ("t0", "comm_done", "compute_done", "gather_done"):
+                marks[nm] = torch.cuda.Event(enable_timing=True)
+            marks["t0"].record(cur)
         events = []
         off = 0
         # filter own views into place, all-gather group by group on the comm stream, integrate behind it
@@ -352,31 +352,21 @@ def main():
                     ctx.apply_depth_threshold_device(n * npix, all_depths[a:b].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH)
                     ctx.set_stream(cur.cuda_stream)
                     off += n
-                if (g1 - g0) == per * world:
-                    dist.all_gather_into_tensor(all_depths[g0:g1].view(-1), all_depths[a:b].view(-1))
-                else:   # ragged last group: plain broadcasts from each owner
-                    for r in range(world):
-                        ra, rb, _ = owned(g0, g1, r)
-                        if rb > ra:
-                            dist.broadcast(all_depths[ra:rb], src=r)
+                D.all_gather_group(dist, all_depths, g0, g1, rank, world)
                 ev = torch.cuda.Event()
                 ev.record(comm_stream)
                 events.append(ev)
+            if args.breakdown:
+                marks["comm_done"].record(comm_stream)
         for (g0, g1), ev in zip(groups, events):
             cur.wait_event(ev)
             ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
         # the finished slabs are gathered once (for contouring on rank 0); slabs may differ by one plane
-        slab = slab_tensor()
-        if rank == 0:
-            full_volume[k0 * N * N:k1 * N * N].copy_(slab)
-            reqs = []
-            for r in range(1, world):
-                a, b = sharding.slab_range(N, r, world)
-                reqs.append(dist.irecv(full_volume[a * N * N:b * N * N], src=r))
-            for q in reqs:
-                q.wait()
-        else:
-            dist.send(slab, dst=0)
+        if args.breakdown:
+            marks["compute_done"].record(cur)
+        D.gather_slabs(dist, slab_tensor(), full_volume, N * N, N, rank, world)
+        if args.breakdown:
+            marks["gather_done"].record(cur)
 
     def barrier():
         if world > 1:
@@ -417,6 +407,11 @@ def main():
     clocks = sampler.stop() if sampler else None
     kernel_ms, kernel_launches = ctx.tsdf_kernel_stats()
     launches = ctx.launch_counter() - launches0
+    if args.breakdown and world > 1:
+        t0 = marks["t0"]
+        print("rank %d breakdown of the last step (ms from its start): all-gathers done %.2f, integration done %.2f, slab gather done %.2f; integration kernels %.2f"
+              % (rank, t0.elapsed_time(marks["comm_done"]), t0.elapsed_time(marks["compute_done"]), t0.elapsed_time(marks["gather_done"]),
+                 kernel_ms / args.steps), file=sys.stderr)
     value = units / (ms_step * 1e-3)
 
     # ---- how much of the work the fast kernel actually evaluated (diagnostic build of the kernel, untimed)

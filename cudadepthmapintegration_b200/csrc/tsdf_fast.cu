@@ -64,12 +64,17 @@ __device__ __forceinline__ void classify_far(double& acc, unsigned& near, double
   asm("{\n\t"
       ".reg .pred pv, pf, pa, pn;\n\t"
       ".reg .f32 df, adf;\n\t"
+      ".reg .b32 shi, zero;\n\t"
+      ".reg .f64 sel;\n\t"
+      "mov.b32 zero, 0;\n\t"
       "sub.rn.f32 df, %3, %4;\n\t"
       "abs.f32 adf, df;\n\t"
       "setp.neu.f32 pv, %4, 0fBF800000;\n\t"
       "setp.gt.and.f32 pf, adf, %5, pv;\n\t"
       "setp.lt.and.f32 pa, df, 0f00000000, pf;\n\t"
-      "@pa add.rn.f64 %0, %0, %2;\n\t"
+      "selp.b32 shi, 0x3FF00000, 0, pa;\n\t"          // 1.0 or 0.0 as a double: one select, then one DFMA
+      "mov.b64 sel, {zero, shi};\n\t"                  // (ptxas turns a predicated DADD into DADD + 2 FSEL)
+      "fma.rn.f64 %0, %2, sel, %0;\n\t"
       "xor.pred pn, pv, pf;\n\t"
       "@pn or.b32 %1, %1, %6;\n\t"
       "}" : "+d"(acc), "+r"(near) : "d"(ner), "f"(fc), "f"(d32), "f"(thr), "r"(bit));
@@ -84,7 +89,8 @@ __device__ __forceinline__ void classify_far(float& acc, unsigned& near, float n
       "setp.neu.f32 pv, %4, 0fBF800000;\n\t"
       "setp.gt.and.f32 pf, adf, %5, pv;\n\t"
       "setp.lt.and.f32 pa, df, 0f00000000, pf;\n\t"
-      "@pa add.rn.f32 %0, %0, %2;\n\t"
+      "selp.f32 df, 0f3F800000, 0f00000000, pa;\n\t"
+      "fma.rn.f32 %0, %2, df, %0;\n\t"
       "xor.pred pn, pv, pf;\n\t"
       "@pn or.b32 %1, %1, %6;\n\t"
       "}" : "+f"(acc), "+r"(near) : "f"(ner), "f"(fc), "f"(d32), "f"(thr), "r"(bit));
@@ -353,35 +359,42 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
     // no predicate, no default value, one sector for the whole warp
     const int rej = (int)(clsSpare - (long long)voff);
 
-    // ---- phase A: classify all FM voxels with the FP32 tier
+    // Two halves of FM/2 voxels, software-pipelined: A(0) B(0) A(1) B(1) C(0) C(1), so that the gathers
+    // of one half are in flight while the other half is classified.
+    constexpr int HM = FM / 2;
     int idx[FM];
-    unsigned need = 0;
-    bool anyv = false;
+    float d32[FM];
+    unsigned need3 = 0;
+    bool anyh[2];
 #pragma unroll
-    for (int m = 0; m < FM; m++)
+    for (int h = 0; h < 2; h++)
     {
-      const float fz = fmaf((float)m, kz, fhz0);
-      const float fx = fmaf((float)m, kx, fnx0);
-      const float fy = fmaf((float)m, ky, fny0);
-      const float r = rcp_approx(fz);
-      const float tu = fmaf(fx, r, kMagic), tv = fmaf(fy, r, kMagic);      // centred pixel, rounded to integer
-      const float pu = tu - kMagic, pv = tv - kMagic;
-      const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);            // distance to that integer
-      const float tx = fmaf(-et.x, r, et.z), ty = fmaf(-et.y, r, et.w);
-      const bool cert = (fz > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
-      const int px = __float_as_int(tu) - pxoff;
-      const int py = __float_as_int(tv) - pyoff;
-      const bool ok = cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H;
-      idx[m] = ok ? px + py * negW : rej;
-      anyv |= ok;
-      if (!cert) need |= 1u << m;
-      if (COUNT) n_t1 += cert ? 1 : 0;
-    }
-    // ---- rare: voxels the FP32 tier could not certify (and every voxel behind the camera plane).
-    // Dynamic m, so that lanes with different m run the same instructions together.
-    if (need)
-    {
-      unsigned need3 = 0;
+      // ---- phase A: classify HM voxels with the FP32 tier
+      unsigned need = 0;
+      bool anyv = false;
+#pragma unroll
+      for (int mm = 0; mm < HM; mm++)
+      {
+        const int m = h * HM + mm;
+        const float fz = fmaf((float)m, kz, fhz0);
+        const float fx = fmaf((float)m, kx, fnx0);
+        const float fy = fmaf((float)m, ky, fny0);
+        const float r = rcp_approx(fz);
+        const float tu = fmaf(fx, r, kMagic), tv = fmaf(fy, r, kMagic);      // centred pixel, rounded to integer
+        const float pu = tu - kMagic, pv = tv - kMagic;
+        const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);            // distance to that integer
+        const float tx = fmaf(-et.x, r, et.z), ty = fmaf(-et.y, r, et.w);
+        const bool cert = (fz > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
+        const int px = __float_as_int(tu) - pxoff;
+        const int py = __float_as_int(tv) - pyoff;
+        const bool ok = cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H;
+        idx[m] = ok ? px + py * negW : rej;
+        anyv |= ok;
+        if (!cert) need |= 1u << m;
+        if (COUNT) n_t1 += cert ? 1 : 0;
+      }
+      // ---- rare: voxels the FP32 tier could not certify (and every voxel behind the camera plane).
+      // Dynamic m, so that lanes with different m run the same instructions together.
       while (need)
       {
         const int m = __ffs(need) - 1;
@@ -401,36 +414,51 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
         }
         if (!okm) id = rej;
 #pragma unroll
-        for (int mm = 0; mm < FM; mm++) if (mm == m) idx[mm] = id;
+        for (int mm = 0; mm < HM; mm++) if (h * HM + mm == m) idx[h * HM + mm] = id;
         anyv |= okm;
       }
-      if (need3)
+      anyh[h] = anyv;
+      // ---- phase B: the half's gathers of the float classification image, all in flight together
+      if (anyv)
       {
 #pragma unroll
-        for (int m = 0; m < FM; m++)
-          if (need3 & (1u << m))
-          {
-            if (COUNT) n_t3++;
-            acc[m] = exact_unit<T>(&g, &c.e[v], depths + npix * v, cls + npix * v, i, j, k0 + m, acc[m]);
-          }
+        for (int mm = 0; mm < HM; mm++) d32[h * HM + mm] = __ldg(cv + idx[h * HM + mm]);
+      }
+      else
+      {
+#pragma unroll
+        for (int mm = 0; mm < HM; mm++) d32[h * HM + mm] = -1.0f;
       }
     }
-    if (!anyv) continue;
-
-    // ---- phase B: all gathers of the float classification image in flight together
-    float d32[FM];
+    if (need3)                                                               // T3, ~1e-9 of the voxels
+    {
 #pragma unroll
-    for (int m = 0; m < FM; m++) d32[m] = __ldg(cv + idx[m]);
+      for (int m = 0; m < FM; m++)
+        if (need3 & (1u << m))
+        {
+          if (COUNT) n_t3++;
+          acc[m] = exact_unit<T>(&g, &c.e[v], depths + npix * v, cls + npix * v, i, j, k0 + m, acc[m]);
+        }
+    }
+    if (!anyh[0] && !anyh[1]) continue;
 
     // ---- phase C: FP32 classification; -1.0f = invalid after the filter (:202).  In front and farther
     // than Delta (certified by the margin in thrfar): -Eta*Rho; behind and farther: 0 (:114-115);
     // everything else that is valid (NaN included) goes to the FP64 band below.
     unsigned near = 0;
 #pragma unroll
-    for (int m = 0; m < FM; m++)
+    for (int h = 0; h < 2; h++)
     {
-      const float fc = PINHOLE ? fmaf((float)m, kz, fhz0) : fmaf((float)m, kc, fcz0);   // camera z (:207)
-      classify_far(acc[m], near, nerT, fc, d32[m], thrfar, 1u << m);
+      if (anyh[h])
+      {
+#pragma unroll
+        for (int mm = 0; mm < HM; mm++)
+        {
+          const int m = h * HM + mm;
+          const float fc = PINHOLE ? fmaf((float)m, kz, fhz0) : fmaf((float)m, kc, fcz0);   // camera z (:207)
+          classify_far(acc[m], near, nerT, fc, d32[m], thrfar, 1u << m);
+        }
+      }
     }
     // ---- the band around the surface: double depth, FP64 potential
     if (near)
