@@ -269,3 +269,72 @@ def test_filter_class_mirrors_reference_api(oracle):
     assert_close(got.reshape(-1), want)
     assert f.GetExecutionTime() > 0
     f.close()
+
+
+# ---- BASELINE.json sizes: size-independent properties (the oracle would take hours here) --------------
+
+def _device_scene(n, n_views, W, H):
+    import torch
+    from cudadepthmapintegration_b200 import synthetic as syn
+    grid = syn.make_grid(n)
+    rp = syn.make_ray_potential(grid)
+    K, RT = syn.make_cameras(n_views, W, H)
+    dev = torch.device("cuda", 0)
+    ds, cs = [], []
+    for v0 in range(0, n_views, 8):
+        d, c, _ = syn.render_views(K[v0:v0 + 8], RT[v0:v0 + 8], W, H, first_view=v0, device=dev,
+                                   depth_noise=0.25 * float(grid.spacing.max()), want_color=False)
+        ds.append(d); cs.append(c)
+    return grid, rp, K, RT, torch.cat(ds), torch.cat(cs)
+
+
+def _integrate_device(ctx, grid, rp, K, RT, d, c, W, H, slab=None, splits=None, cull=1):
+    import torch
+    ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_AUTO)
+    ctx.set_option(_lib.DMI_OPT_CULL, cull)
+    ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
+    if slab is not None:
+        ctx.set_slab(*slab)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        ctx.volume_begin(None, np.float64)
+        n = K.shape[0]
+        bounds = [0, n] if splits is None else [0] + list(splits) + [n]
+        npix = W * H
+        for a, b in zip(bounds, bounds[1:]):
+            ctx.volume_integrate_device(b - a, d.data_ptr() + a * npix * 8, c.data_ptr() + a * npix * 8, 0.14, K[a:b], RT[a:b])
+        ptr, nbytes = ctx.volume_device_ptr()
+
+        class _H:
+            pass
+        h = _H()
+        h.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        out = torch.as_tensor(h, device=d.device).clone()
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_stream(None)
+        ctx.set_option(_lib.DMI_OPT_CULL, 1)
+    return out
+
+
+def test_full_size_properties_512_cube_1080p(gpu_ctx):
+    """512^3 cells x 96 views of 1920x1080 (the grid and image size of BASELINE.json configs[3]):
+    splitting the view list across calls, splitting the grid into z-slabs and switching the brick
+    culling off must not change a single bit; the volume must also be physically sensible."""
+    import torch
+    n, nv, W, H = 512, 96, 1920, 1080
+    grid, rp, K, RT, d, c = _device_scene(n, nv, W, H)
+    whole = _integrate_device(gpu_ctx, grid, rp, K, RT, d, c, W, H)
+    assert torch.equal(whole, _integrate_device(gpu_ctx, grid, rp, K, RT, d, c, W, H, splits=[7, 64, 65]))
+    assert torch.equal(whole, _integrate_device(gpu_ctx, grid, rp, K, RT, d, c, W, H, cull=0))
+    parts = [_integrate_device(gpu_ctx, grid, rp, K, RT, d, c, W, H, slab=s) for s in [(0, 100), (100, 101), (101, 317), (317, 512)]]
+    assert torch.equal(whole, torch.cat(parts))
+    vol = whole.view(n, n, n)
+    assert torch.isfinite(vol).all()
+    # far outside the sphere, seen in free space by many views: strictly negative; the centre of the sphere is
+    # behind the surface for every view: exactly zero
+    assert vol[n // 2, n // 2, 5].item() < 0 and vol[5, n // 2, n // 2].item() < 0
+    assert vol[n // 2, n // 2, n // 2].item() == 0.0
+    # just inside the surface along +x: positive (behind the surface within Thick)
+    r_in = int(n / 2 + (1.0 - 1.5 * float(grid.spacing[0])) / float(grid.spacing[0]))
+    assert vol[n // 2, n // 2, r_in].item() > 0
