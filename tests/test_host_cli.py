@@ -1,0 +1,85 @@
+"""The C++ host mirror (csrc/host): list-file / .krtd / .vti parsing without a GPU, and the CLI end to end
+on the GPU against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cudadepthmapintegration_b200 import dataset_io
+from tests.scenes import Scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "cudadepthmapintegration_b200", "dmi_cli")
+
+
+def _need_cli():
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "cudadepthmapintegration_b200", "csrc")], check=True, capture_output=True)
+
+
+def test_parsers_read_what_was_written(tmp_path):
+    _need_cli()
+    s = Scene(8, 3, 40, 30, rotate_deg=10.0)
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT, ascii_views=(1,))
+    r = subprocess.run([CLI, "inspect", "--vti", str(tmp_path / "vtiList.txt"), "--krtd", str(tmp_path / "kList.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "views 3 krtd 3"
+    for v, line in enumerate(lines[1:]):
+        t = line.split()
+        assert int(t[3]) == 40 and int(t[5]) == 30
+        assert float(t[7]) == pytest.approx(float(s.depths[v].sum()), rel=1e-13)
+        assert float(t[9]) == pytest.approx(float(s.best_cost[v].sum()), rel=1e-13)
+        assert int(t[11]) == int(s.colors[v].astype(np.int64).sum())
+        assert int(t[13]) == int((s.depths[v] == -1).sum())
+        K = np.array([float(x) for x in t[15:31]])
+        RT = np.array([float(x) for x in t[32:48]])
+        assert np.array_equal(K, s.K[v]) and np.array_equal(RT, s.RT[v])      # repr() round-trips doubles
+
+
+def test_cli_rejects_the_reference_cli_error_cases(tmp_path):
+    _need_cli()
+    base = [CLI, "reconstruction", "--gridOrigin", "-1", "-1", "-1", "--gridEnd", "1", "1", "1", "--gridDims", "9",
+            "--dataFolder", str(tmp_path), "--outputGridFilename", str(tmp_path / "o.mhd")]
+    # Delta < Thick and Eta outside [0,1] are argument errors (Reconstruction/main.cxx:270-271)
+    assert subprocess.run(base + ["--rayThick", "0.5", "--rayDelta", "0.3"], capture_output=True).returncode != 0
+    assert subprocess.run(base + ["--rayThick", "0.1", "--rayDelta", "0.3", "--rayEta", "1.5"], capture_output=True).returncode != 0
+    # non-orthogonal grid vectors (:363-382)
+    assert subprocess.run(base + ["--rayThick", "0.1", "--rayDelta", "0.3", "--gridVecX", "1", "1", "0"], capture_output=True).returncode != 0
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_against_oracle(tmp_path, oracle):
+    _need_cli()
+    from cudadepthmapintegration_b200 import synthetic as syn
+    s = Scene(24, 5, 64, 48, rotate_deg=30.0, depth_noise=0.25)
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT)
+    gm = s.grid.matrix.reshape(4, 4)
+    out = tmp_path / "vol.mhd"
+    cmd = [CLI, "reconstruction", "--gridDims", "25", "25", "25", "--gridOrigin", *[repr(float(x)) for x in s.grid.origin],
+           "--gridEnd", *[repr(float(o + 25 * sp)) for o, sp in zip(s.grid.origin, s.grid.spacing)],
+           "--gridVecX", *[repr(float(x)) for x in gm[0, :3]], "--gridVecY", *[repr(float(x)) for x in gm[1, :3]],
+           "--gridVecZ", *[repr(float(x)) for x in gm[2, :3]], "--dataFolder", str(tmp_path),
+           "--rayThick", repr(s.rp.thick), "--rayRho", repr(s.rp.rho), "--rayEta", repr(s.rp.eta), "--rayDelta", repr(s.rp.delta),
+           "--threshBestCost", "0.14", "--outputGridFilename", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(str(tmp_path / "vol.raw"), dtype=np.float64)
+    # the CLI derives spacing = (end - origin) / dims like the reference (main.cxx:318-323): rebuild the same grid
+    spacing = (np.array([float(o + 25 * sp) for o, sp in zip(s.grid.origin, s.grid.spacing)]) - s.grid.origin) / 25.0
+    grid = syn.Grid((24, 24, 24), s.grid.origin, spacing, s.grid.matrix)
+    want = oracle.tsdf_integrate(grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, np.zeros(24 ** 3))
+    assert np.array_equal(got != 0, want != 0)
+    assert np.abs(got - want).max() <= 1e-6
+    # coloration through the CLI
+    pts = syn.fibonacci_sphere_points(2000)
+    pts.tofile(str(tmp_path / "pts.f32"))
+    r = subprocess.run([CLI, "coloration", "--input", str(tmp_path / "pts.f32"), "--output", str(tmp_path / "col"),
+                        "--krtd", str(tmp_path / "kList.txt"), "--vti", str(tmp_path / "vtiList.txt")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    wmean, wmed, wnb = oracle.colorize(pts, s.colors, s.K, s.RT, s.W, s.H)
+    assert np.array_equal(np.fromfile(str(tmp_path / "col.nb.i32"), dtype=np.int32), wnb)
+    assert np.array_equal(np.fromfile(str(tmp_path / "col.median.u8"), dtype=np.uint8).reshape(-1, 3), wmed)
+    assert np.array_equal(np.fromfile(str(tmp_path / "col.mean.u8"), dtype=np.uint8).reshape(-1, 3), wmean)
