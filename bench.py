@@ -55,6 +55,10 @@ def parse_args():
     ap.add_argument("--no-coloration", action="store_true")
     ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
     ap.add_argument("--group", type=int, default=128, help="views per all-gather group (N>1)")
+    ap.add_argument("--exchange", default="ce", choices=["ce", "nccl"],
+                    help="N>1 view exchange: 'ce' = copy-engine pushes into CUDA-IPC mapped peer buffers (no SMs), 'nccl' = all-gather")
+    ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
+                    help="N=1 diagnostic: integrate only the z-slab that RANK of WORLD would own (value counts that slab's pairs)")
     ap.add_argument("--breakdown", action="store_true", help="N>1: print the comm / compute / gather spans of the last step to stderr")
     ap.add_argument("--color-points", type=int, default=2000000)
     ap.add_argument("--color-views", type=int, default=200)
@@ -277,6 +281,8 @@ def main():
     rp = syn.make_ray_potential(grid)
     K, RT = syn.make_cameras(V, W, H)
     k0, k1 = sharding.slab_range(N, rank, world)
+    if args.emulate_rank and world == 1:
+        k0, k1 = sharding.slab_range(N, args.emulate_rank[0], args.emulate_rank[1])
     slab_cells = (k1 - k0) * N * N
 
     ctx = Context(local_rank)
@@ -289,14 +295,30 @@ def main():
     # ---- view ownership: groups of G views; inside a group rank r owns a contiguous G/world share, so
     # that an in-place all-gather of the group's region of the resident buffer assembles it.
     groups = D.view_groups(V, args.group if world > 1 else V, world)
-    G = groups[0][1] - groups[0][0]
+    G = max(b - a for a, b in groups)
 
     def owned(g0, g1, r=rank):
         return D.owned_range(g0, g1, r, world)
 
     # ---- generate this rank's views on its GPU (stands for "loaded from the files it owns")
     noise = 0.25 * float(grid.spacing.max())
-    all_depths = torch.empty((V, H, W), dtype=torch.float64, device=dev) if world > 1 else None
+    all_depths, peer_ptr, own_ptr, fence = None, None, None, None
+    if world > 1 and args.exchange == "ce":
+        # the resident view buffer is allocated by the library (plain cudaMalloc) so that every rank can map
+        # every other rank's buffer through CUDA IPC and PUSH its share with the copy engines over NVLink
+        own_ptr = ctx.device_malloc(V * npix * 8)
+
+        class _Buf:
+            pass
+        hb = _Buf()
+        hb.__cuda_array_interface__ = {"shape": (V, H, W), "typestr": "<f8", "data": (own_ptr, False), "version": 3}
+        all_depths = torch.as_tensor(hb, device=dev)
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_get_handle(own_ptr))
+        peer_ptr = [own_ptr if r == rank else ctx.ipc_open_handle(handles[r]) for r in range(world)]
+        fence = torch.zeros(1, dtype=torch.float32, device=dev)
+    elif world > 1:
+        all_depths = torch.empty((V, H, W), dtype=torch.float64, device=dev)
     my_idx = np.array(D.owned_views(V, args.group if world > 1 else V, rank, world), dtype=np.int64)
     nmine = len(my_idx)
     my_depths = torch.empty((nmine, H, W), dtype=torch.float64, device=dev)
@@ -343,6 +365,8 @@ def main():
         off = 0
         # filter own views into place, all-gather group by group on the comm stream, integrate behind it
         with torch.cuda.stream(comm_stream):
+            if peer_ptr is not None:
+                dist.all_reduce(fence)          # every rank is done reading the previous step's views
             for (g0, g1) in groups:
                 a, b, per = owned(g0, g1)
                 n = b - a
@@ -352,15 +376,31 @@ def main():
                     ctx.apply_depth_threshold_device(n * npix, all_depths[a:b].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH)
                     ctx.set_stream(cur.cuda_stream)
                     off += n
-                D.all_gather_group(dist, all_depths, g0, g1, rank, world)
+                if peer_ptr is None:
+                    D.all_gather_group(dist, all_depths, g0, g1, rank, world)
+                else:
+                    if n > 0:
+                        ctx.set_stream(comm_stream.cuda_stream)
+                        for r in range(1, world):      # staggered order: every link busy, no hot receiver
+                            dst = (rank + r) % world
+                            ctx.memcpy_device_async(peer_ptr[dst] + a * npix * 8, own_ptr + a * npix * 8, n * npix * 8)
+                        ctx.set_stream(cur.cuda_stream)
+                    dist.all_reduce(fence)      # all shares of this group have landed everywhere
                 ev = torch.cuda.Event()
                 ev.record(comm_stream)
                 events.append(ev)
             if args.breakdown:
                 marks["comm_done"].record(comm_stream)
+        marks["groups"] = []
         for (g0, g1), ev in zip(groups, events):
             cur.wait_event(ev)
+            if args.breakdown:
+                ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ga.record(cur)
             ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
+            if args.breakdown:
+                gb.record(cur)
+                marks["groups"].append((ga, gb))
         # the finished slabs are gathered once (for contouring on rank 0); slabs may differ by one plane
         if args.breakdown:
             marks["compute_done"].record(cur)
@@ -388,7 +428,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0].item()) / steps, float(ms[1].item()) / steps
 
-    units = float(N) ** 3 * V
+    units = float(N) ** 3 * V if not (args.emulate_rank and world == 1) else float(slab_cells) * V
 
     # ---- FP peaks for the roofline (MEASURED_PEAKS.json has no FP32/FP64 vector peak)
     fp64_peak = ctx.measure_fp_peak(0, 300.0)
@@ -412,6 +452,8 @@ def main():
         print("rank %d breakdown of the last step (ms from its start): all-gathers done %.2f, integration done %.2f, slab gather done %.2f; integration kernels %.2f"
               % (rank, t0.elapsed_time(marks["comm_done"]), t0.elapsed_time(marks["compute_done"]), t0.elapsed_time(marks["gather_done"]),
                  kernel_ms / args.steps), file=sys.stderr)
+        print("rank %d per-group integration spans (start, duration ms): %s" % (rank, " ".join(
+            "(%.1f,%.1f)" % (t0.elapsed_time(ga), ga.elapsed_time(gb)) for ga, gb in marks["groups"])), file=sys.stderr)
     value = units / (ms_step * 1e-3)
 
     # ---- how much of the work the fast kernel actually evaluated (diagnostic build of the kernel, untimed)
@@ -477,7 +519,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H}, best-cost threshold {THRESH}, f64 volume",
-                       "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views all-gathered in groups of {G}" if world > 1 else ""),
+                       "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views exchanged in groups of {G} ({'copy-engine pushes over CUDA IPC' if args.exchange == 'ce' else 'NCCL all-gather'})" if world > 1 else ""),
                        "l2": "inputs (%.1f GB per step) exceed L2; no flush needed" % (algorithmic_bytes(N, V, W, H) / 1e9),
                        "kernel": args.kernel, "cull": args.cull},
             "roofline": roofline, "gpu_launches": launches, "clocks": clocks,

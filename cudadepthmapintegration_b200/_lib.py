@@ -65,6 +65,12 @@ _PROTOTYPES = {
     "dmi_colorize": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dmi_colorize_device": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dmi_color_kernel_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_ll)]),
+    "dmi_device_malloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "dmi_device_free": (C.c_int, [_vp, _vp]),
+    "dmi_ipc_get_handle": (C.c_int, [_vp, _vp, C.c_char_p]),
+    "dmi_ipc_open_handle": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "dmi_ipc_close_handle": (C.c_int, [_vp, _vp]),
+    "dmi_memcpy_device_async": (C.c_int, [_vp, _vp, _vp, _sz]),
     "dmi_measure_fp_peak": (C.c_int, [_vp, _i, _d, _pd]),
     "dmi_launch_counter": (C.c_int, [_vp, C.POINTER(_ll)]),
 }

@@ -1,29 +1,54 @@
-// Mesh coloration kernel for sm_100a: one warp per mesh point.
+// Mesh coloration kernel for sm_100a: one warp colours Q mesh points at a time.
 //
 // The reference (Coloration/MeshColoration.cxx:140-192) walks points x views on one CPU thread,
 // pushes the gathered r,g,b into three std::vector<double>, then copies + std::sorts each for the
-// median (Sources/Helper.h:174-187).  Here a warp owns a point; its lanes stride over the views,
-// project the point with the reference's exact double arithmetic, gather the colour bytes and count
-// them into three 256-bin histograms in shared memory (colours are uchar, so a counting histogram
-// IS the sorted multiset).  Sum, count and both middle order statistics come out of one warp-wide
-// prefix scan per channel -- all integer, hence bit-exact:
+// median (Sources/Helper.h:174-187).  Here the lanes of a warp stride over the views; each lane keeps
+// ITS view's projection in registers for a tile of 32 views and projects the warp's Q points with it,
+// gathers the colour bytes and counts them into per-point 3 x 256-bin histograms in shared memory
+// (colours are uchar, so a counting histogram IS the sorted multiset).  Sum, count and both middle
+// order statistics come out of one warp-wide prefix scan per channel -- all integer, hence bit-exact:
 //   mean   = (int sum) / n      == (unsigned char)(sum / (double)n)                 (:176-180)
 //   median = odd n: v[n/2]; even n: (v[n/2] + v[n/2-1]) / 2 truncated               (Helper.h:179-186)
+//
+// Which pixel a point falls on (ReconstructionData::TransformWorldToDepthMapPosition, ~37 uncontracted
+// FP64 operations + 2 IEEE divisions in the reference) is decided by the same three certified tiers as
+// the integration kernel (DESIGN.md "certification"):
+//   T1  FP32: composed 3x4 rows (9 FFMA), MUFU.RCP, magic-number rounding, distance to the integer
+//       against 0.5 - (E*|r| + c0) with E = kE * (A*m + B) from per-view coefficient sums and the
+//       point's max |coordinate| m.  Mesh points are float32 (vtkPoints' default), hence exact inputs.
+//   T2  FP64 composed rows + residual test of the candidate (margin 2^-44 of the magnitudes the
+//       reference's own evaluation order goes through).
+//   T3  the reference's operation sequence (project_exact), on ties / near-zero denominators / double
+//       points that are not float-representable.
+// There is no z-sign test and no depth test in the reference (a point behind the camera still projects):
+// all tiers work with |d.z|.
 #include "dmi_internal.cuh"
+
+#include <cmath>
+#include <algorithm>
 
 namespace dmi {
 
-constexpr int kColorWarps = 8;     // warps (= points in flight) per CTA
+constexpr int kColorWarps = 8;     // warps per CTA
 constexpr int kBins = 256;
+constexpr float kMagicC = 12582912.0f;
+constexpr int kMagicBitsC = 0x4B400000;
 
-// TransformWorldToDepthMapPosition (Sources/ReconstructionData.cxx:169-182) for one view:
+__device__ __forceinline__ float rcp_approx_c(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// T3 -- TransformWorldToDepthMapPosition (Sources/ReconstructionData.cxx:169-182) for one view:
 //   cam = RT * p    vtkTransform::TransformPoint   m0*x + m1*y + m2*z + m3
 //   d   = K3 * cam  vtkTransform::TransformVector  m0*x + m1*y + m2*z
 //   px = (int)std::round(d.x / d.z), py likewise, x86 conversion (anything unrepresentable -> INT_MIN,
-//   which the bounds test at MeshColoration.cxx:158-163 rejects).  No z-sign test, no depth test.
-// Returns true and the pixel when it falls inside [0,W) x [0,H).
-__device__ __forceinline__ bool project_exact(const double* __restrict__ m, int stride, int v,
-                                              double x, double y, double z, int W, int H, int& px, int& py)
+//   which the bounds test at MeshColoration.cxx:158-163 rejects).
+// Returns the storage index (H-1-py)*W + px of GetColorValue (ReconstructionData.cxx:107-115), or -1.
+__device__ __noinline__ int project_exact(const double* __restrict__ m, int stride, int v,
+                                          double x, double y, double z, int W, int H)
 {
   double r[21];
 #pragma unroll
@@ -37,10 +62,37 @@ __device__ __forceinline__ bool project_exact(const double* __restrict__ m, int 
   const double u = round(__ddiv_rn(dx, dz));
   const double w = round(__ddiv_rn(dy, dz));
   // accept iff the x86 conversion would give a value in [0,W) / [0,H): NaN and +-inf fail the compares
-  if (!(u >= 0.0 && u < (double)W && w >= 0.0 && w < (double)H)) return false;
-  px = (int)u;
-  py = (int)w;
-  return true;
+  if (!(u >= 0.0 && u < (double)W && w >= 0.0 && w < (double)H)) return -1;
+  return (H - 1 - (int)w) * W + (int)u;
+}
+
+// T2, falling through to T3.  pu, pv: T1's candidate (centred integer pixel as float), or NaN for "none".
+template <typename XYZ>
+__device__ __noinline__ int project_slow(const ColorViews& views, int v, const XYZ* __restrict__ xyz, size_t p, float mf,
+                                         float pu, float pv, int W, int H)
+{
+  // the point is re-read here so that the hot loop keeps only its float copy in registers
+  const double x = (double)xyz[3 * p + 0], y = (double)xyz[3 * p + 1], z = (double)xyz[3 * p + 2], m = (double)mf;
+  const ColorViewT2& V = views.t2[v];
+  const double dz = fma(x, V.dz[0], fma(y, V.dz[1], fma(z, V.dz[2], V.dz[3])));
+  const double adz = fabs(dz);
+  const double mz = fma(V.mza, m, V.mzb), m2 = fma(V.m2a, m, V.m2b);
+  const double half = 0.5 * adz;
+  double cu = (double)pu, cv = (double)pv;
+  if (adz > mz && m2 < 0.01 * half && fabs(cu) < 4194304.0 && fabs(cv) < 4194304.0)
+  {
+    const double sg = dz < 0.0 ? -1.0 : 1.0;
+    double su = sg * fma(-cu, dz, fma(x, V.nx[0], fma(y, V.nx[1], fma(z, V.nx[2], V.nx[3]))));   // (u' - cu) * |dz|
+    double sv = sg * fma(-cv, dz, fma(x, V.ny[0], fma(y, V.ny[1], fma(z, V.ny[2], V.ny[3]))));
+    if (su >= half + m2) { cu += 1.0; su -= adz; } else if (su <= -half - m2) { cu -= 1.0; su += adz; }
+    if (sv >= half + m2) { cv += 1.0; sv -= adz; } else if (sv <= -half - m2) { cv -= 1.0; sv += adz; }
+    if (fabs(su) < half - m2 && fabs(sv) < half - m2)
+    {
+      const int px = (int)cu + views.cxc, py = (int)cv + views.cyc;
+      return ((unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H) ? (H - 1 - py) * W + px : -1;
+    }
+  }
+  return project_exact(views.m, views.stride, v, x, y, z, W, H);
 }
 
 // Order statistic helper: given this lane's 8 consecutive bins (counts c[0..7], bins 8*lane..8*lane+7)
@@ -61,33 +113,11 @@ __device__ __forceinline__ int select_rank(const unsigned c[8], unsigned before,
   return __shfl_sync(0xffffffffu, found, src);
 }
 
-// Projection with the view already in registers (r[0..11] = RT rows 0..2, r[12..20] = K 3x3).
-__device__ __forceinline__ bool project_exact_regs(const double (&r)[21], double x, double y, double z,
-                                                   int W, int H, int& px, int& py)
-{
-  const double cx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(r[0], x), __dmul_rn(r[1], y)), __dmul_rn(r[2], z)), r[3]);
-  const double cy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(r[4], x), __dmul_rn(r[5], y)), __dmul_rn(r[6], z)), r[7]);
-  const double cz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(r[8], x), __dmul_rn(r[9], y)), __dmul_rn(r[10], z)), r[11]);
-  const double dx = __dadd_rn(__dadd_rn(__dmul_rn(r[12], cx), __dmul_rn(r[13], cy)), __dmul_rn(r[14], cz));
-  const double dy = __dadd_rn(__dadd_rn(__dmul_rn(r[15], cx), __dmul_rn(r[16], cy)), __dmul_rn(r[17], cz));
-  const double dz = __dadd_rn(__dadd_rn(__dmul_rn(r[18], cx), __dmul_rn(r[19], cy)), __dmul_rn(r[20], cz));
-  const double u = round(__ddiv_rn(dx, dz));
-  const double w = round(__ddiv_rn(dy, dz));
-  // accept iff the x86 conversion would give a value in [0,W) / [0,H): NaN and +-inf fail the compares
-  if (!(u >= 0.0 && u < (double)W && w >= 0.0 && w < (double)H)) return false;
-  px = (int)u;
-  py = (int)w;
-  return true;
-}
-
-// One warp colours Q points at a time.  For each tile of 32 views a lane loads ITS view once (21 doubles,
-// coalesced from the SoA matrix array) and projects the Q points with it, so the matrix traffic is
-// amortised Q times and the Q independent projections hide each other's FP64 / gather latency.
 // Histograms: 3 channels x 256 bins x 16-bit counters per point, two bins per 32-bit word (shared-memory
 // atomics are 32-bit); requires nViews < 65536, which the launcher checks.
 template <typename XYZ, int Q>
-__global__ void __launch_bounds__(32 * kColorWarps)
-colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, ColorViews views,
+__global__ void __launch_bounds__(32 * kColorWarps, 2)
+colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_constant__ ColorViews views,
                 const uint8_t* __restrict__ colors, int W, int H,
                 uint8_t* __restrict__ mean, uint8_t* __restrict__ median, int32_t* __restrict__ nb)
 {
@@ -96,6 +126,8 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, ColorViews views,
   const size_t npix = (size_t)W * H;
   const size_t batches = (nPoints + Q - 1) / Q;
   const size_t warpsTotal = (size_t)gridDim.x * kColorWarps;
+  const int pxoff = kMagicBitsC - views.cxc, pyoff = kMagicBitsC - views.cyc;
+  const float T = views.T;
 
   for (size_t bt = (size_t)blockIdx.x * kColorWarps + warp; bt < batches; bt += warpsTotal)
   {
@@ -105,29 +137,46 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, ColorViews views,
     for (int q = 0; q < Q * 3 * kBins / 2 / 32; q++) hw[q * 32 + lane] = 0u;
     __syncwarp();
     // vtkPoints::GetPoint: stored type promoted to double (MeshColoration.cxx:147-148)
-    double x[Q], y[Q], z[Q];
+    float xf[Q], yf[Q], zf[Q], mf[Q];
+    bool fexact[Q];
     unsigned s0[Q], s1[Q], s2[Q], n[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++)
     {
       const size_t p = min(p0 + q, nPoints - 1);
-      x[q] = (double)xyz[3 * p + 0]; y[q] = (double)xyz[3 * p + 1]; z[q] = (double)xyz[3 * p + 2];
+      const double xd = (double)xyz[3 * p + 0], yd = (double)xyz[3 * p + 1], zd = (double)xyz[3 * p + 2];
+      xf[q] = (float)xd; yf[q] = (float)yd; zf[q] = (float)zd;
+      // T1 needs exact float inputs and a finite magnitude bound
+      fexact[q] = (double)xf[q] == xd && (double)yf[q] == yd && (double)zf[q] == zd;
+      mf[q] = fmaxf(fabsf(xf[q]), fmaxf(fabsf(yf[q]), fabsf(zf[q])));
       s0[q] = s1[q] = s2[q] = n[q] = 0u;
     }
     for (int v = lane; v < views.nViews; v += 32)
     {
-      double r[21];
-#pragma unroll
-      for (int e = 0; e < 21; e++) r[e] = __ldg(views.m + (size_t)e * views.stride + v);
+      // this lane's view, FP32 form: 80 bytes
+      const float4* fp = reinterpret_cast<const float4*>(views.fast + v);
+      const float4 rx = __ldg(fp + 0), ry = __ldg(fp + 1), rz = __ldg(fp + 2), pe = __ldg(fp + 3), pz = __ldg(fp + 4);
       const uint8_t* img = colors + npix * 3 * (size_t)v;
 #pragma unroll
       for (int q = 0; q < Q; q++)
       {
-        int px, py;
-        if (project_exact_regs(r, x[q], y[q], z[q], W, H, px, py))
+        const float fz = fmaf(xf[q], rz.x, fmaf(yf[q], rz.y, fmaf(zf[q], rz.z, rz.w)));
+        const float fx = fmaf(xf[q], rx.x, fmaf(yf[q], rx.y, fmaf(zf[q], rx.z, rx.w)));
+        const float fy = fmaf(xf[q], ry.x, fmaf(yf[q], ry.y, fmaf(zf[q], ry.z, ry.w)));
+        const float r = rcp_approx_c(fz), ar = fabsf(r);
+        const float tu = fmaf(fx, r, kMagicC), tv = fmaf(fy, r, kMagicC);
+        const float pu = tu - kMagicC, pv = tv - kMagicC;
+        const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);
+        const float Ex = fmaf(pe.x, mf[q], pe.y), Ey = fmaf(pe.z, mf[q], pe.w), zm = fmaf(pz.x, mf[q], pz.y);
+        const float tx = fmaf(-Ex, ar, T), ty = fmaf(-Ey, ar, T);
+        const bool cert = fexact[q] && (fabsf(fz) > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
+        const int px = __float_as_int(tu) - pxoff, py = __float_as_int(tv) - pyoff;
+        int idx = (cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H) ? (H - 1 - py) * W + px : -1;
+        if (!cert)
+          idx = project_slow<XYZ>(views, v, xyz, min(p0 + q, nPoints - 1), mf[q], fexact[q] ? pu : NAN, fexact[q] ? pv : NAN, W, H);
+        if (idx >= 0)
         {
-          // GetColorValue: Color[(H-1-py)*W + px] (ReconstructionData.cxx:107-115)
-          const uint8_t* c = img + ((size_t)(H - 1 - py) * W + px) * 3;
+          const uint8_t* c = img + (size_t)idx * 3;
           const unsigned cr = c[0], cg = c[1], cb = c[2];
           atomicAdd(&hist[warp][q][0][cr >> 1], 1u << ((cr & 1) * 16));
           atomicAdd(&hist[warp][q][1][cg >> 1], 1u << ((cg & 1) * 16));
@@ -211,6 +260,70 @@ cudaError_t launch_colorize(size_t nPoints, const void* d_xyz, int xyzType, Colo
     colorize_kernel<float, Q><<<(unsigned)blocks, 32 * kColorWarps, 0, s>>>(
         nPoints, (const float*)d_xyz, views, d_colors, W, H, d_mean, d_median, d_nb);
   return cudaGetLastError();
+}
+
+// ---- host side: composition of one view ---------------------------------------------------------
+
+static float upf(double x)
+{
+  float f = (float)x;
+  if ((double)f < x) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+float color_threshold_T(int W, int H)
+{
+  const double U1 = std::max(W, H) / 2.0 + 2.0;
+  const double c0 = (4.0 / 3.0) * 1.05 * std::ldexp(1.0, -23) * U1 + std::ldexp(1.0, -20);
+  float T = (float)(0.5 - c0);
+  if ((double)T > 0.5 - c0) T = nextafterf(T, -INFINITY);
+  return T;
+}
+
+// D = K3 * RT(3x4) in long double; rows nx = D0 - cxc*D2, ny = D1 - cyc*D2, dz = D2 over (x, y, z, 1).
+void compose_color_view(const double* K16, const double* RT16, int cxc, int cyc, int W, int H,
+                        ColorViewFast* fo, ColorViewT2* t2)
+{
+  typedef long double L;
+  L D[3][4];
+  double Aabs[3] = {0, 0, 0}, Babs[3] = {0, 0, 0};        // magnitudes the REFERENCE's evaluation goes through
+  for (int r = 0; r < 3; r++)
+  {
+    for (int j = 0; j < 4; j++)
+    {
+      D[r][j] = 0;
+      for (int c = 0; c < 3; c++) D[r][j] += (L)K16[4 * r + c] * (L)RT16[4 * c + j];
+    }
+    for (int c = 0; c < 3; c++)
+    {
+      Aabs[r] += std::fabs(K16[4 * r + c]) * (std::fabs(RT16[4 * c + 0]) + std::fabs(RT16[4 * c + 1]) + std::fabs(RT16[4 * c + 2]));
+      Babs[r] += std::fabs(K16[4 * r + c]) * std::fabs(RT16[4 * c + 3]);
+    }
+  }
+  const L cc[2] = {(L)cxc, (L)cyc};
+  double* rows[2] = {t2->nx, t2->ny};
+  for (int r = 0; r < 2; r++)
+    for (int j = 0; j < 4; j++) rows[r][j] = (double)(D[r][j] - cc[r] * D[2][j]);
+  for (int j = 0; j < 4; j++) t2->dz[j] = (double)D[2][j];
+  for (int j = 0; j < 4; j++) { fo->nx[j] = (float)t2->nx[j]; fo->ny[j] = (float)t2->ny[j]; fo->dz[j] = (float)t2->dz[j]; }
+  auto A = [](const double* r) { return std::fabs(r[0]) + std::fabs(r[1]) + std::fabs(r[2]); };
+  const double U1 = std::max(W, H) / 2.0 + 2.0;
+  // T1: |f - true| <= 7 * 2^-24 * (A*m + B) per row (4 coefficient roundings + 3 FMA roundings), E = (4/3)*(dn + U1*dz)
+  const double kE = (4.0 / 3.0) * 7.0 * 1.01 * std::ldexp(1.0, -24);
+  fo->pax = upf(kE * (A(t2->nx) + U1 * A(t2->dz))); fo->pbx = upf(kE * (std::fabs(t2->nx[3]) + U1 * std::fabs(t2->dz[3])));
+  fo->pay = upf(kE * (A(t2->ny) + U1 * A(t2->dz))); fo->pby = upf(kE * (std::fabs(t2->ny[3]) + U1 * std::fabs(t2->dz[3])));
+  // |fz| > zm must imply dz_err / |fz| <= 1/4
+  const double kZ = 4.0 * 7.0 * 1.01 * std::ldexp(1.0, -24);
+  fo->zma = upf(kZ * A(t2->dz)); fo->zmb = upf(kZ * std::fabs(t2->dz[3]));
+  fo->pad[0] = fo->pad[1] = 0.f;
+  // T2 margins: 2^-44 of the reference's intermediate magnitudes (|K3| * |RT| sums), composed rows included
+  const double k2 = std::ldexp(1.0, -44);
+  const double Ax = Aabs[0] + std::fabs((double)cxc) * Aabs[2], Bx = Babs[0] + std::fabs((double)cxc) * Babs[2];
+  const double Ay = Aabs[1] + std::fabs((double)cyc) * Aabs[2], By = Babs[1] + std::fabs((double)cyc) * Babs[2];
+  t2->m2a = k2 * (std::max(Ax, Ay) + U1 * Aabs[2]);
+  t2->m2b = k2 * (std::max(Bx, By) + U1 * Babs[2]);
+  t2->mza = k2 * Aabs[2];
+  t2->mzb = k2 * Babs[2] + 1e-300;
 }
 
 }  // namespace dmi

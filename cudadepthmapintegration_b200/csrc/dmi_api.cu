@@ -536,23 +536,39 @@ int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[8])
 
 // ---- coloration ---------------------------------------------------------------------------------
 
-static int pack_color_views(dmi_ctx* ctx, int nViews, const double* K, const double* RT, dmi::ColorViews* out)
+static int pack_color_views(dmi_ctx* ctx, int nViews, const double* K, const double* RT, int W, int H, dmi::ColorViews* out)
 {
   const int stride = (nViews + 31) & ~31;
-  std::vector<double> m((size_t)21 * stride, 0.0);
+  const size_t exactBytes = (size_t)21 * stride * 8;
+  const size_t fastOff = (exactBytes + 15) & ~(size_t)15;
+  const size_t fastBytes = sizeof(dmi::ColorViewFast) * (size_t)nViews;
+  const size_t t2Off = (fastOff + fastBytes + 15) & ~(size_t)15;
+  const size_t total = t2Off + sizeof(dmi::ColorViewT2) * (size_t)nViews;
+  std::vector<unsigned char> host(total, 0);
+  double* m = reinterpret_cast<double*>(host.data());
+  dmi::ColorViewFast* fast = reinterpret_cast<dmi::ColorViewFast*>(host.data() + fastOff);
+  dmi::ColorViewT2* t2 = reinterpret_cast<dmi::ColorViewT2*>(host.data() + t2Off);
+  const int cxc = W / 2, cyc = H / 2;
   for (int v = 0; v < nViews; v++)
   {
     for (int e = 0; e < 12; e++) m[(size_t)e * stride + v] = RT[16 * (size_t)v + e];
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) m[(size_t)(12 + r * 3 + c) * stride + v] = K[16 * (size_t)v + r * 4 + c];
+    dmi::compose_color_view(K + 16 * (size_t)v, RT + 16 * (size_t)v, cxc, cyc, W, H, &fast[v], &t2[v]);
   }
-  DMI_CK(ctx->c_mats.ensure(m.size() * 8));
-  // pageable source: the copy has consumed `m` by the time cudaMemcpyAsync returns
-  DMI_CK(cudaMemcpyAsync(ctx->c_mats.p, m.data(), m.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  DMI_CK(ctx->c_mats.ensure(total));
+  // pageable source: the copy has consumed `host` by the time cudaMemcpyAsync returns
+  DMI_CK(cudaMemcpyAsync(ctx->c_mats.p, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
   DMI_CK(cudaStreamSynchronize(ctx->stream));
-  out->m = (const double*)ctx->c_mats.p;
+  const unsigned char* base = (const unsigned char*)ctx->c_mats.p;
+  out->m = (const double*)base;
+  out->fast = (const dmi::ColorViewFast*)(base + fastOff);
+  out->t2 = (const dmi::ColorViewT2*)(base + t2Off);
   out->nViews = nViews;
   out->stride = stride;
+  out->cxc = cxc;
+  out->cyc = cyc;
+  out->T = dmi::color_threshold_T(W, H);
   return DMI_OK;
 }
 
@@ -570,7 +586,8 @@ int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyz
   DMI_REQUIRE(d_xyz && d_colors && d_mean && d_median && d_nb, "null argument");
   DMI_CK(cudaSetDevice(ctx->device));
   dmi::ColorViews views;
-  int rc = pack_color_views(ctx, nViews, K, RT, &views);
+  DMI_REQUIRE(W < (1 << 21) && H < (1 << 21), "image dims must be below 2^21");
+  int rc = pack_color_views(ctx, nViews, K, RT, W, H, &views);
   if (rc != DMI_OK) return rc;
   EventSpan span = ctx->color_stats.open();
   DMI_CK(cudaEventRecord(span.a, ctx->stream));
@@ -621,6 +638,62 @@ int dmi_color_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches)
   if (ms) *ms = ctx->color_stats.drain(); else ctx->color_stats.drain();
   if (launches) *launches = ctx->color_stats.launches;
   ctx->color_stats.launches = 0;
+  return DMI_OK;
+}
+
+// ---- shared device buffers -----------------------------------------------------------------------
+
+int dmi_device_malloc(dmi_ctx* ctx, size_t bytes, void** d_ptr)
+{
+  if (!ctx || !d_ptr) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return DMI_OK;
+}
+
+int dmi_device_free(dmi_ctx* ctx, void* d_ptr)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(cudaFree(d_ptr));
+  return DMI_OK;
+}
+
+int dmi_ipc_get_handle(dmi_ctx* ctx, void* d_ptr, unsigned char handle[64])
+{
+  if (!ctx || !d_ptr || !handle) return DMI_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DMI_CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  DMI_CK(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, 64);
+  return DMI_OK;
+}
+
+int dmi_ipc_open_handle(dmi_ctx* ctx, const unsigned char handle[64], void** d_ptr)
+{
+  if (!ctx || !d_ptr || !handle) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  DMI_CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DMI_OK;
+}
+
+int dmi_ipc_close_handle(dmi_ctx* ctx, void* d_ptr)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(cudaIpcCloseMemHandle(d_ptr));
+  return DMI_OK;
+}
+
+int dmi_memcpy_device_async(dmi_ctx* ctx, void* d_dst, const void* d_src, size_t bytes)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  DMI_REQUIRE(bytes == 0 || (d_dst && d_src), "null argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  if (bytes) DMI_CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, ctx->stream));
   return DMI_OK;
 }
 

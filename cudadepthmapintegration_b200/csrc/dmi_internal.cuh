@@ -102,12 +102,30 @@ cudaError_t launch_depth_threshold(double* d_depths, const double* d_cost, size_
                                    cudaStream_t s);
 
 // coloration
-struct ColorViews   // device SoA: m[e][v], e in 0..20 = RT rows 0..2 (12) then K 3x3 (9)
+struct alignas(16) ColorViewFast   // T1 form of one view: rows over (x, y, z, 1), float
 {
-  const double* m;
-  int nViews;
-  int stride;       // padded view count
+  float nx[4], ny[4], dz[4];
+  float pax, pbx, pay, pby;        // E_x = pax * m + pbx, E_y = pay * m + pby (m = max |coordinate| of the point)
+  float zma, zmb, pad[2];          // zm = zma * m + zmb
 };
+struct ColorViewT2                 // T2 form: the same rows in double + margins
+{
+  double nx[4], ny[4], dz[4];
+  double m2a, m2b, mza, mzb;
+};
+struct ColorViews
+{
+  const double* m;                 // T3: SoA m[e][v], e in 0..20 = RT rows 0..2 (12) then K 3x3 (9)
+  const ColorViewFast* fast;
+  const ColorViewT2* t2;
+  int nViews;
+  int stride;                      // padded view count of m
+  int cxc, cyc;
+  float T;
+};
+float color_threshold_T(int W, int H);
+void compose_color_view(const double* K16, const double* RT16, int cxc, int cyc, int W, int H,
+                        ColorViewFast* fast, ColorViewT2* t2);
 cudaError_t launch_colorize(size_t nPoints, const void* d_xyz, int xyzType, ColorViews views,
                             const uint8_t* d_colors, int W, int H, uint8_t* d_mean, uint8_t* d_median,
                             int32_t* d_nb, cudaStream_t s);

@@ -11,10 +11,24 @@ from __future__ import annotations
 from . import sharding
 
 
-def view_groups(n_views: int, group: int, world: int):
-    """[(g0, g1)] consecutive groups of views; the group size is a multiple of the world size."""
+def view_groups(n_views: int, group: int, world: int, ramp: bool = True):
+    """[(g0, g1)] consecutive groups of views; every group size is a multiple of the world size.  With
+    `ramp` the first groups are smaller (G/4, G/4, G/2), so that integration starts after a short first
+    exchange instead of waiting for a full group."""
     g = max(world, (max(group, 1) // world) * world)
-    return [(g0, min(n_views, g0 + g)) for g0 in range(0, n_views, g)]
+    sizes = []
+    if ramp and world > 1:
+        for f in (4, 4, 2):
+            q = max(world, (g // f // world) * world)
+            if q < g:
+                sizes.append(q)
+    out, g0, i = [], 0, 0
+    while g0 < n_views:
+        q = sizes[i] if i < len(sizes) else g
+        out.append((g0, min(n_views, g0 + q)))
+        g0 += q
+        i += 1
+    return out
 
 
 def owned_range(g0: int, g1: int, rank: int, world: int):

@@ -209,6 +209,31 @@ class Context:
         self._ck(self._lib.dmi_color_kernel_stats(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    # -- shared device buffers (multi-GPU view exchange over the copy engines) --------------------
+    def device_malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.dmi_device_malloc(self._h, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, ptr: int):
+        self._ck(self._lib.dmi_device_free(self._h, C.c_void_p(int(ptr))))
+
+    def ipc_get_handle(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self._lib.dmi_ipc_get_handle(self._h, C.c_void_p(int(ptr)), buf))
+        return buf.raw
+
+    def ipc_open_handle(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.dmi_ipc_open_handle(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return int(p.value)
+
+    def ipc_close_handle(self, ptr: int):
+        self._ck(self._lib.dmi_ipc_close_handle(self._h, C.c_void_p(int(ptr))))
+
+    def memcpy_device_async(self, dst: int, src: int, nbytes: int):
+        self._ck(self._lib.dmi_memcpy_device_async(self._h, C.c_void_p(int(dst)), C.c_void_p(int(src)), int(nbytes)))
+
     # -- measurement -----------------------------------------------------------------------------
     def launch_counter(self) -> int:
         n = C.c_longlong()

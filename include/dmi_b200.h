@@ -160,6 +160,23 @@ int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyz
                         uint8_t* d_mean, uint8_t* d_median, int32_t* d_nbProjected);
 int dmi_color_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
 
+/* ---- device buffers shared between the per-GPU processes (multi-GPU view exchange) --------------- */
+
+/* Plain cudaMalloc / cudaFree on the context's device: buffers allocated here can be exported to the
+ * other ranks' processes with CUDA IPC, so that the view all-gather can run on the COPY ENGINES over
+ * NVLink (dmi_memcpy_device_async into a peer's mapped buffer) instead of on SMs that the integration
+ * kernel needs. */
+int dmi_device_malloc(dmi_ctx* ctx, size_t bytes, void** d_ptr);
+int dmi_device_free(dmi_ctx* ctx, void* d_ptr);
+/* 64-byte cudaIpcMemHandle_t of a dmi_device_malloc buffer / mapping of a peer's handle (peer access is
+ * enabled lazily) / unmapping. */
+int dmi_ipc_get_handle(dmi_ctx* ctx, void* d_ptr, unsigned char handle[64]);
+int dmi_ipc_open_handle(dmi_ctx* ctx, const unsigned char handle[64], void** d_ptr);
+int dmi_ipc_close_handle(dmi_ctx* ctx, void* d_ptr);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on the context's stream; either side may be a
+ * mapped peer buffer. */
+int dmi_memcpy_device_async(dmi_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+
 /* ---- measurement helpers ------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched on behalf of the context since dmi_create. */
