@@ -79,7 +79,7 @@ struct dmi_ctx
   long long opt_kernel = DMI_TSDF_KERNEL_AUTO, opt_chunk = 0;
   long long total_launches = 0;
   dmi::FastChunk fast_chunk{};
-  DevBuf counters, cls, tiles, viewscratch;
+  DevBuf counters, cls, tiles, viewscratch, maskscratch;
   bool counters_on = false;
   bool opt_cull = true;
   std::string err;
@@ -165,7 +165,7 @@ int dmi_destroy(dmi_ctx* ctx)
   }
   ctx->filtered.release();
   ctx->counters.release();
-  ctx->cls.release(); ctx->tiles.release(); ctx->viewscratch.release();
+  ctx->cls.release(); ctx->tiles.release(); ctx->viewscratch.release(); ctx->maskscratch.release();
   ctx->c_xyz.release(); ctx->c_colors.release(); ctx->c_mats.release();
   ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release();
   ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
@@ -343,6 +343,7 @@ static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_dep
   DMI_CK(ctx->cls.ensure(((size_t)group * npix + 1) * 4));   // + the spare slot holding -1.0f
   DMI_CK(ctx->tiles.ensure((size_t)group * tilesPerView * 4));
   DMI_CK(ctx->viewscratch.ensure(sizeof(dmi::ViewFast) * dmi::kFastChunk));
+  DMI_CK(ctx->maskscratch.ensure(dmi::tsdf_fast_mask_bytes(g)));
   dmi::FastChunk* c = &ctx->fast_chunk;
   dmi::fill_fast_chunk_constants(g, c);
   for (int g0 = 0; g0 < nViews; g0 += group)
@@ -367,11 +368,11 @@ static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_dep
       DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths + npix * (g0 + v0), (const float*)ctx->cls.p + npix * v0,
                                    (long long)(npix * (size_t)(gn - v0)),
                                    (const float*)ctx->tiles.p + tilesPerView * v0, ctx->opt_cull,
-                                   (dmi::ViewFast*)ctx->viewscratch.p, ctx->vol.p,
+                                   (dmi::ViewFast*)ctx->viewscratch.p, (unsigned*)ctx->maskscratch.p, ctx->vol.p,
                                    ctx->vol_type, ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr,
                                    ctx->stream));
       ctx->tsdf_stats.launches++;
-      ctx->total_launches += 2;                           // the view-staging kernel and the integration kernel
+      ctx->total_launches += ctx->opt_cull ? 3 : 2;       // view staging, supertile culling, integration
     }
   }
   return DMI_OK;

@@ -153,17 +153,18 @@ struct __align__(16) ViewSm
 
 struct BrickBox { bool valid; float ux, uy; int tx0, tx1, ty0, ty1; };
 
-// Projected bounding box of the brick for one view (8 corners; the projection of a box with hz > 0 is
-// the convex hull of its projected corners).  Returns false when the box cannot be trusted (brick too
-// close to the camera plane).  Margins: 1.5 px + the FP32 evaluation error (<= 0.25 px inside the
-// image by the E*r test, proportional to |u| outside).
+// Projected bounding box of a box of voxels for one view (8 corners; the projection of a box with hz > 0
+// is the convex hull of its projected corners).  (ei, ej, ek) = extents - 1 in voxels; (lx, ly, lz) bound
+// the local terms.  Returns false when the box cannot be trusted (too close to the camera plane).
+// Margins: 1.5 px + the FP32 evaluation error (<= 0.25 px inside the image by the E*r test,
+// proportional to |u| outside).
 __device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c, float fbx, float fby, float fbz,
+                                          float ei, float ej, float ek, float lx, float ly, float lz,
                                           float zlo, int W, int H, BrickBox& o, bool& outside)
 {
   outside = false;
-  const float Eg = c.k3 * (fmaxf(fabsf(fbx) + 3.f * V.lx, fabsf(fby) + 3.f * V.ly) + c.umax1g * (fabsf(fbz) + 3.f * V.lz));
+  const float Eg = c.k3 * (fmaxf(fabsf(fbx) + 3.f * lx, fabsf(fby) + 3.f * ly) + c.umax1g * (fabsf(fbz) + 3.f * lz));
   if (!(zlo > V.zm) || !(Eg * rcp_approx(zlo) <= 0.24f)) return false;
-  const float ei = (float)(FBI - 1), ej = (float)(FBJ - 1), ek = (float)(FM - 1);
   const float zi = V.fhz[0] * ei, zj = V.fhz[1] * ej, zk = V.fhz[2] * ek;
   const float xi = V.fnx[0] * ei, xj = V.fnx[1] * ej, xk = V.fnx[2] * ek;
   const float yi = V.fny[0] * ei, yj = V.fny[1] * ej, yk = V.fny[2] * ek;
@@ -210,13 +211,99 @@ __device__ __forceinline__ float footprint_dmax(const TilePyramid& pyr, const fl
   return fmaxf(fmaxf(a, bq), fmaxf(cq, dq));
 }
 
+// Everything the pre-pass needs to know about (box of voxels, view): FP64 base of the rows at the box
+// origin rounded to float, |u| bounds over the box, and whether the view can be CULLED for the whole box:
+// every voxel behind the camera (:177), outside the image (:192-197), over tiles without a valid pixel
+// (:202), or farther than Delta BEHIND every valid depth it can meet (rayPotential returns 0, :114-115).
+struct BoxEval { bool keep; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs; };
+
+template <bool PINHOLE>
+__device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& c, const TilePyramid& pyr,
+                                            const float* __restrict__ td, int i0, int j0, int k0,
+                                            float ei, float ej, float ek, float lx, float ly, float lz, float lc,
+                                            int W, int H, bool cull)
+{
+  BoxEval o;
+  o.fbx = __double2float_rn(affine(V.nx, (double)i0, (double)j0, (double)k0));
+  o.fby = __double2float_rn(affine(V.ny, (double)i0, (double)j0, (double)k0));
+  o.fbz = __double2float_rn(affine(V.hz, (double)i0, (double)j0, (double)k0));
+  o.fbc = PINHOLE ? o.fbz : __double2float_rn(affine(V.cz, (double)i0, (double)j0, (double)k0));
+  o.Ux = c.umax1g; o.Uy = c.umax1g;
+  // range of h.z and of camera z over the box (affine: extremes are sums of per-axis extremes)
+  const float zi = V.fhz[0] * ei, zj = V.fhz[1] * ej, zk = V.fhz[2] * ek;
+  const float zslack = 4e-7f * (fabsf(o.fbz) + 3.f * lz);
+  const float zlo = o.fbz + fminf(zi, 0.f) + fminf(zj, 0.f) + fminf(zk, 0.f) - zslack;
+  const float zhi = o.fbz + fmaxf(zi, 0.f) + fmaxf(zj, 0.f) + fmaxf(zk, 0.f) + zslack;
+  float clo = zlo, chi = zhi;
+  if (!PINHOLE)
+  {
+    const float ci = V.fcz[0] * ei, cj = V.fcz[1] * ej, ck = V.fcz[2] * ek;
+    const float cslack = 4e-7f * (fabsf(o.fbc) + 3.f * lc);
+    clo = o.fbc + fminf(ci, 0.f) + fminf(cj, 0.f) + fminf(ck, 0.f) - cslack;
+    chi = o.fbc + fmaxf(ci, 0.f) + fmaxf(cj, 0.f) + fmaxf(ck, 0.f) + cslack;
+  }
+  o.czmaxabs = fmaxf(fabsf(clo), fabsf(chi));
+  o.keep = true;
+  BrickBox box; box.valid = false;
+  bool outside = false;
+  const bool boxed = brick_box(V, c, o.fbx, o.fby, o.fbz, ei, ej, ek, lx, ly, lz, zlo, W, H, box, outside);
+  if (boxed) { o.Ux = fminf(c.umax1g, box.ux + 1.f); o.Uy = fminf(c.umax1g, box.uy + 1.f); }
+  if (cull)
+  {
+    if (zhi < -V.zm) o.keep = false;
+    else if (boxed && outside) o.keep = false;
+    else if (boxed && box.valid)
+    {
+      const float dmax = footprint_dmax(pyr, td, box);
+      const float thr = c.delta_up + 1e-6f * o.czmaxabs;
+      if (dmax == -INFINITY || clo - dmax > thr) o.keep = false;
+    }
+  }
+  return o;
+}
+
+// First culling level: one thread per (supertile of 64 x 32 x 32 voxels, view); bit v of masks[st] = view v
+// may contribute to supertile st.  A brick only examines the views its supertile kept.
+template <bool PINHOLE>
+__global__ void __launch_bounds__(256)
+supertile_cull_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
+                      const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr,
+                      const ViewFast* __restrict__ gviews, int nbi, int nbj, int nbk, unsigned* __restrict__ masks, int nst)
+{
+  static_assert(kFastChunk == 64, "two ballots per supertile");
+  const int st = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int v = threadIdx.x & 63;
+  bool keep = false;
+  if (st < nst && v < c.n)
+  {
+    const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ;
+    const int i0 = (st % nsi) * FSI * FBI, j0 = ((st / nsi) % nsj) * FSJ * FBJ, k0 = g.k0 + (st / (nsi * nsj)) * FSK * FM;
+    const ViewFast& V = gviews[v];
+    const float ei = (float)(FSI * FBI - 1), ej = (float)(FSJ * FBJ - 1), ek = (float)(FSK * FM - 1);
+    const float lx = 1.001f * (fabsf(V.fnx[0]) * ei + fabsf(V.fnx[1]) * ej + fabsf(V.fnx[2]) * ek);
+    const float ly = 1.001f * (fabsf(V.fny[0]) * ei + fabsf(V.fny[1]) * ej + fabsf(V.fny[2]) * ek);
+    const float lz = 1.001f * (fabsf(V.fhz[0]) * ei + fabsf(V.fhz[1]) * ej + fabsf(V.fhz[2]) * ek);
+    const float lc = 1.001f * (fabsf(V.fcz[0]) * ei + fabsf(V.fcz[1]) * ej + fabsf(V.fcz[2]) * ek);
+    keep = eval_box<PINHOLE>(V, c, pyr, tileDmax + (size_t)v * pyr.perView, i0, j0, k0, ei, ej, ek, lx, ly, lz, lc,
+                             g.W, g.H, true).keep;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if ((threadIdx.x & 31) == 0 && st < nst) masks[2 * st + ((threadIdx.x >> 5) & 1)] = bal;
+}
+
+__device__ __forceinline__ int nth_set_bit64(unsigned lo, unsigned hi, int n)
+{
+  const int nlo = __popc(lo);
+  return n < nlo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - nlo + 1);
+}
+
 template <typename T, bool PINHOLE, bool COUNT>
 __global__ void __launch_bounds__(FT)
 tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
                  const double* __restrict__ depths, const float* __restrict__ cls,
                  const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
-                 long long clsSpare, const ViewFast* __restrict__ gviews, T* __restrict__ vol,
-                 int nbi, int nbj, int nbk, FastCounters* counters)
+                 long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
+                 T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters)
 {
   static_assert(kFastChunk <= FT, "one pre-pass thread per view");
   __shared__ ViewSm s_view[kFastChunk];
@@ -234,56 +321,24 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int W = g.W, H = g.H;
 
-  // ---- pre-pass: the even threads prepare one view each (all four warps take part, so that none waits
-  // long at the barrier; lane order = view order, which the ballot compaction below preserves)
+  // ---- pre-pass: the views the supertile kept are dealt to consecutive threads, one each (dense lanes;
+  // thread order = view order, which the ballot compaction below preserves).  The view is read from the
+  // GLOBAL copy of the chunk: every lane wants a different one, which a constant-bank load would
+  // serialise 32 ways.
   {
-    static_assert(2 * kFastChunk <= FT, "one even thread per view");
-    const int v = threadIdx.x >> 1;
-    bool keep = false;
-    float fbx = 0.f, fby = 0.f, fbz = 0.f, fbc = 0.f, Ux = c.umax1g, Uy = c.umax1g, czmaxabs = 0.f;
-    // the pre-pass reads its view from the GLOBAL copy of the chunk: every lane wants a different view,
-    // which a constant-bank load would serialise 32 ways
-    const ViewFast& V = gviews[min(v, c.n - 1)];
-    if (!(threadIdx.x & 1) && v < c.n)
-    {
-      fbx = __double2float_rn(affine(V.nx, (double)i0, (double)j0, (double)k0));
-      fby = __double2float_rn(affine(V.ny, (double)i0, (double)j0, (double)k0));
-      fbz = __double2float_rn(affine(V.hz, (double)i0, (double)j0, (double)k0));
-      fbc = PINHOLE ? fbz : __double2float_rn(affine(V.cz, (double)i0, (double)j0, (double)k0));
-      const float ei = (float)(FBI - 1), ej = (float)(FBJ - 1), ek = (float)(FM - 1);
-      // range of h.z and of camera z over the brick (affine: extremes are sums of per-axis extremes)
-      const float zi = V.fhz[0] * ei, zj = V.fhz[1] * ej, zk = V.fhz[2] * ek;
-      const float zslack = 4e-7f * (fabsf(fbz) + 3.f * V.lz);
-      const float zlo = fbz + fminf(zi, 0.f) + fminf(zj, 0.f) + fminf(zk, 0.f) - zslack;
-      const float zhi = fbz + fmaxf(zi, 0.f) + fmaxf(zj, 0.f) + fmaxf(zk, 0.f) + zslack;
-      float clo = zlo, chi = zhi;
-      if (!PINHOLE)
-      {
-        const float ci = V.fcz[0] * ei, cj = V.fcz[1] * ej, ck = V.fcz[2] * ek;
-        const float cslack = 4e-7f * (fabsf(fbc) + 3.f * V.lc);
-        clo = fbc + fminf(ci, 0.f) + fminf(cj, 0.f) + fminf(ck, 0.f) - cslack;
-        chi = fbc + fmaxf(ci, 0.f) + fmaxf(cj, 0.f) + fmaxf(ck, 0.f) + cslack;
-      }
-      czmaxabs = fmaxf(fabsf(clo), fabsf(chi));
-      keep = true;
-      BrickBox box; box.valid = false;
-      bool outside = false;
-      const bool boxed = brick_box(V, c, fbx, fby, fbz, zlo, W, H, box, outside);
-      if (boxed) { Ux = fminf(c.umax1g, box.ux + 1.f); Uy = fminf(c.umax1g, box.uy + 1.f); }
-      if (cull)
-      {
-        if (zhi < -V.zm) keep = false;                        // the whole brick is behind the camera (:177)
-        else if (boxed && outside) keep = false;              // ... projects outside the image (:192-197)
-        else if (boxed && box.valid)
-        {
-          const float dmax = footprint_dmax(pyr, tileDmax + (size_t)v * pyr.perView, box);
-          const float thr = c.delta_up + 1e-6f * czmaxabs;
-          // no valid pixel under the brick (:202), or every voxel farther than Delta BEHIND every valid
-          // depth it can meet: rayPotential returns 0 (:114-115)
-          if (dmax == -INFINITY || clo - dmax > thr) keep = false;
-        }
-      }
-    }
+    unsigned mlo = 0xffffffffu, mhi = 0xffffffffu;
+    if (c.n < 64) { mlo = c.n >= 32 ? 0xffffffffu : ((1u << c.n) - 1u); mhi = c.n > 32 ? ((1u << (c.n - 32)) - 1u) : 0u; }
+    if (cull && stmasks) { mlo &= __ldg(stmasks + 2 * st); mhi &= __ldg(stmasks + 2 * st + 1); }
+    const int ncand = __popc(mlo) + __popc(mhi);
+    const bool have = (int)threadIdx.x < ncand;
+    const int v = have ? nth_set_bit64(mlo, mhi, threadIdx.x) : 0;
+    const ViewFast& V = gviews[v];
+    BoxEval e;
+    e.keep = false;
+    if (have)
+      e = eval_box<PINHOLE>(V, c, pyr, tileDmax + (size_t)v * pyr.perView, i0, j0, k0, (float)(FBI - 1), (float)(FBJ - 1),
+                            (float)(FM - 1), V.lx, V.ly, V.lz, V.lc, W, H, cull != 0);
+    const bool keep = e.keep;
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_cnt[w] = __popc(bal);
     __syncthreads();
@@ -292,12 +347,12 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
       int pos = __popc(bal & ((1u << lane) - 1u));
       for (int q = 0; q < w; q++) pos += s_cnt[q];
       ViewSm& S = s_view[pos];
-      const float Ex = c.k3 * ((fabsf(fbx) + 3.f * V.lx) + Ux * (fabsf(fbz) + 3.f * V.lz));
-      const float Ey = c.k3 * ((fabsf(fby) + 3.f * V.ly) + Uy * (fabsf(fbz) + 3.f * V.lz));
-      S.base = make_float4(fbx, fby, fbz, V.zm);
-      S.et = make_float4(Ex, Ey, 0.5f - (Ux * c.kq + 9.6e-7f), 0.5f - (Uy * c.kq + 9.6e-7f));
-      S.cx = make_float4(V.fnx[0], V.fnx[1], V.fnx[2], c.delta_up + 1e-6f * czmaxabs);
-      S.cy = make_float4(V.fny[0], V.fny[1], V.fny[2], fbc);
+      const float Ex = c.k3 * ((fabsf(e.fbx) + 3.f * V.lx) + e.Ux * (fabsf(e.fbz) + 3.f * V.lz));
+      const float Ey = c.k3 * ((fabsf(e.fby) + 3.f * V.ly) + e.Uy * (fabsf(e.fbz) + 3.f * V.lz));
+      S.base = make_float4(e.fbx, e.fby, e.fbz, V.zm);
+      S.et = make_float4(Ex, Ey, 0.5f - (e.Ux * c.kq + 9.6e-7f), 0.5f - (e.Uy * c.kq + 9.6e-7f));
+      S.cx = make_float4(V.fnx[0], V.fnx[1], V.fnx[2], c.delta_up + 1e-6f * e.czmaxabs);
+      S.cy = make_float4(V.fny[0], V.fny[1], V.fny[2], e.fbc);
       S.cz = make_float4(V.fhz[0], V.fhz[1], V.fhz[2], 0.f);
       S.cc = make_float4(V.fcz[0], V.fcz[1], V.fcz[2], 0.f);
       S.czr[0] = V.cz[0]; S.czr[1] = V.cz[1]; S.czr[2] = V.cz[2]; S.czr[3] = V.cz[3];
@@ -525,18 +580,32 @@ __global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant_
 template <typename T, bool PINHOLE>
 static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths,
                            const float* d_cls, const float* d_tileDmax, const TilePyramid& pyr, bool cull,
-                           long long clsSpare, const ViewFast* d_views, T* d_vol, int nbi, int nbj, int nbk,
-                           FastCounters* d_counters, cudaStream_t s)
+                           long long clsSpare, const ViewFast* d_views, unsigned* d_masks, T* d_vol, int nbi, int nbj,
+                           int nbk, FastCounters* d_counters, cudaStream_t s)
 {
+  if (cull && d_masks)
+  {
+    const int nst = (int)(grid / (FSI * FSJ * FSK));
+    supertile_cull_kernel<PINHOLE><<<(nst + 3) / 4, 256, 0, s>>>(g, c, d_tileDmax, pyr, d_views, nbi, nbj, nbk, d_masks, nst);
+  }
+  const unsigned* masks = (cull && d_masks) ? d_masks : nullptr;
   if (d_counters)
-    tsdf_fast_kernel<T, PINHOLE, true><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, d_vol, nbi, nbj, nbk, d_counters);
+    tsdf_fast_kernel<T, PINHOLE, true><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, d_vol, nbi, nbj, nbk, d_counters);
   else
-    tsdf_fast_kernel<T, PINHOLE, false><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, d_vol, nbi, nbj, nbk, nullptr);
+    tsdf_fast_kernel<T, PINHOLE, false><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, d_vol, nbi, nbj, nbk, nullptr);
+}
+
+size_t tsdf_fast_mask_bytes(const GridParams& g)
+{
+  const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
+  const size_t nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
+  return std::max<size_t>(8, nsi * nsj * nsk * 8);
 }
 
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
-                             ViewFast* d_viewScratch, void* d_vol, int scalarType, FastCounters* d_counters, cudaStream_t s)
+                             ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
+                             FastCounters* d_counters, cudaStream_t s)
 {
   const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
   if (nbi <= 0 || nbj <= 0 || nbk <= 0 || c.n <= 0) return cudaSuccess;
@@ -548,13 +617,13 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
   const ViewFast* d_views = d_viewScratch;
   if (scalarType == 1)
   {
-    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
-    else launch_variant<double, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
+    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
+    else launch_variant<double, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
   }
   else
   {
-    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
-    else launch_variant<float, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
+    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
+    else launch_variant<float, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
   }
   return cudaGetLastError();
 }
