@@ -560,12 +560,29 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
 
   if (COUNT && counters)
   {
-    atomicAdd(&counters->t1_certified, n_t1);
-    atomicAdd(&counters->t2_entered, n_t2);
-    atomicAdd(&counters->t3_entered, n_t3);
-    atomicAdd(&counters->delta_guard, n_dg);
-    atomicAdd(&counters->near_band, n_nb);
-    atomicAdd(&counters->units, (unsigned long long)FM * nsurv);
+    // one atomic per warp and counter (the lanes that returned early above are simply absent)
+    const unsigned act = __activemask();
+    unsigned long long vals[6] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)FM * nsurv};
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+    {
+      unsigned long long x = vals[q];
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        const unsigned long long y = __shfl_xor_sync(act, x, o);
+        if ((act >> ((lane ^ o) & 31)) & 1u) x += y;
+      }
+      vals[q] = x;
+    }
+    if (lane == (__ffs(act) - 1))
+    {
+      atomicAdd(&counters->t1_certified, vals[0]);
+      atomicAdd(&counters->t2_entered, vals[1]);
+      atomicAdd(&counters->t3_entered, vals[2]);
+      atomicAdd(&counters->delta_guard, vals[3]);
+      atomicAdd(&counters->near_band, vals[4]);
+      atomicAdd(&counters->units, vals[5]);
+    }
   }
 }
 
