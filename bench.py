@@ -303,10 +303,20 @@ def main():
     # ---- generate this rank's views on its GPU (stands for "loaded from the files it owns")
     noise = 0.25 * float(grid.spacing.max())
     all_depths, peer_ptr, own_ptr, fence = None, None, None, None
+    cls_ptr = tile_ptr = None
     if world > 1 and args.exchange == "ce":
-        # the resident view buffer is allocated by the library (plain cudaMalloc) so that every rank can map
-        # every other rank's buffer through CUDA IPC and PUSH its share with the copy engines over NVLink
-        own_ptr = ctx.device_malloc(V * npix * 8)
+        # the resident view buffers are allocated by the library (plain cudaMalloc) so that every rank can map
+        # every other rank's buffers through CUDA IPC and PUSH its share with the copy engines over NVLink.
+        # One allocation: [depth f64 V*npix][classification f32, per group: n*npix + 4 spare][tile pyramids f32]
+        ncls, ntile = ctx.prepared_view_sizes()
+        cls_off, acc = {}, 0
+        for (g0, g1) in groups:
+            cls_off[g0] = acc
+            acc += (g1 - g0) * ncls + 4
+        depth_bytes = V * npix * 8
+        cls_bytes = (acc * 4 + 255) // 256 * 256
+        own_ptr = ctx.device_malloc(depth_bytes + cls_bytes + V * ntile * 4)
+        cls_ptr, tile_ptr = own_ptr + depth_bytes, own_ptr + depth_bytes + cls_bytes
 
         class _Buf:
             pass
@@ -317,6 +327,11 @@ def main():
         dist.all_gather_object(handles, ctx.ipc_get_handle(own_ptr))
         peer_ptr = [own_ptr if r == rank else ctx.ipc_open_handle(handles[r]) for r in range(world)]
         fence = torch.zeros(1, dtype=torch.float32, device=dev)
+        # the spare "invalid" slot after each group's classification images is written once, locally
+        minus1 = torch.full((4,), -1.0, dtype=torch.float32, device=dev)
+        for (g0, g1) in groups:
+            ctx.memcpy_device_async(cls_ptr + (cls_off[g0] + (g1 - g0) * ncls) * 4, minus1.data_ptr(), 16)
+        ctx.synchronize()
     elif world > 1:
         all_depths = torch.empty((V, H, W), dtype=torch.float64, device=dev)
     my_idx = np.array(D.owned_views(V, args.group if world > 1 else V, rank, world), dtype=np.int64)
@@ -370,21 +385,31 @@ def main():
             for (g0, g1) in groups:
                 a, b, per = owned(g0, g1)
                 n = b - a
-                if n > 0:
-                    all_depths[a:b].copy_(my_depths[off:off + n])
-                    ctx.set_stream(comm_stream.cuda_stream)
-                    ctx.apply_depth_threshold_device(n * npix, all_depths[a:b].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH)
-                    ctx.set_stream(cur.cuda_stream)
-                    off += n
                 if peer_ptr is None:
+                    if n > 0:
+                        all_depths[a:b].copy_(my_depths[off:off + n])
+                        ctx.set_stream(comm_stream.cuda_stream)
+                        ctx.apply_depth_threshold_device(n * npix, all_depths[a:b].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH)
+                        ctx.set_stream(cur.cuda_stream)
+                        off += n
                     D.all_gather_group(dist, all_depths, g0, g1, rank, world)
                 else:
                     if n > 0:
+                        # the owner prepares its views ONCE (filter -> float classification image + tile pyramid)
+                        # and pushes depth, classification and pyramid to every rank, itself included
                         ctx.set_stream(comm_stream.cuda_stream)
+                        c_rel = (cls_off[g0] + (a - g0) * ncls) * 4
+                        ctx.prepare_views_device(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
+                                                 cls_ptr + c_rel, -1, tile_ptr + a * ntile * 4)
+                        ctx.memcpy_device_async(own_ptr + a * npix * 8, my_depths[off:off + n].data_ptr(), n * npix * 8)
                         for r in range(1, world):      # staggered order: every link busy, no hot receiver
                             dst = (rank + r) % world
-                            ctx.memcpy_device_async(peer_ptr[dst] + a * npix * 8, own_ptr + a * npix * 8, n * npix * 8)
+                            base = peer_ptr[dst]
+                            ctx.memcpy_device_async(base + a * npix * 8, my_depths[off:off + n].data_ptr(), n * npix * 8)
+                            ctx.memcpy_device_async(base + depth_bytes + c_rel, cls_ptr + c_rel, n * ncls * 4)
+                            ctx.memcpy_device_async(base + depth_bytes + cls_bytes + a * ntile * 4, tile_ptr + a * ntile * 4, n * ntile * 4)
                         ctx.set_stream(cur.cuda_stream)
+                        off += n
                     dist.all_reduce(fence)      # all shares of this group have landed everywhere
                 ev = torch.cuda.Event()
                 ev.record(comm_stream)
@@ -397,7 +422,11 @@ def main():
             if args.breakdown:
                 ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ga.record(cur)
-            ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
+            if peer_ptr is None:
+                ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
+            else:
+                ctx.volume_integrate_prepared(g1 - g0, own_ptr + g0 * npix * 8, cls_ptr + cls_off[g0] * 4, (g1 - g0) * ncls,
+                                              tile_ptr + g0 * ntile * 4, K[g0:g1], RT[g0:g1])
             if args.breakdown:
                 gb.record(cur)
                 marks["groups"].append((ga, gb))
@@ -455,6 +484,14 @@ def main():
         print("rank %d per-group integration spans (start, duration ms): %s" % (rank, " ".join(
             "(%.1f,%.1f)" % (t0.elapsed_time(ga), ga.elapsed_time(gb)) for ga, gb in marks["groups"])), file=sys.stderr)
     value = units / (ms_step * 1e-3)
+    # bit-pattern digest of the finished volume (untimed): equal across --gpus N when the slabs concatenate exactly
+    final = full_volume if world > 1 else slab_tensor()
+    digest = None
+    if rank == 0:
+        bits = final.view(torch.int64)
+        w = torch.arange(1, bits.numel() + 1, dtype=torch.int64, device=dev)
+        digest = "%016x" % (int((bits * w).sum().item()) & 0xFFFFFFFFFFFFFFFF)
+        del w
 
     # ---- how much of the work the fast kernel actually evaluated (diagnostic build of the kernel, untimed)
     tiers = None
@@ -523,6 +560,7 @@ def main():
                        "l2": "inputs (%.1f GB per step) exceed L2; no flush needed" % (algorithmic_bytes(N, V, W, H) / 1e9),
                        "kernel": args.kernel, "cull": args.cull},
             "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
+            "volume_digest": digest,
         }
         if e2e is not None:
             line["e2e"] = e2e
@@ -569,7 +607,7 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
             my_cost.copy_(h_cost, non_blocking=True)
             step_device()
             h_vol.copy_(slab_tensor(), non_blocking=True)
-        api = "per rank: H2D of its share of the views, dmi_volume_integrate_device after the NCCL all-gather, D2H of its slab"
+        api = "per rank: H2D of its share of the views, owner-side preparation + exchange, integration of its z-slab, D2H of its slab"
         h2d = int(2 * nmine * npix * 8)
     step()
     ms, wall = timed(step, steps)

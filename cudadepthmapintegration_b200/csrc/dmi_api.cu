@@ -326,6 +326,43 @@ static int integrate_exact_resident(dmi_ctx* ctx, int nViews, const double* d_de
   return DMI_OK;
 }
 
+// Fast kernel over views that are ALREADY prepared (classification images + tile pyramids, see
+// launch_prepare_views): composes the per-view rows and launches chunk by chunk.
+static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const float* d_cls, long long clsSpare,
+                                   const float* d_tiles, const double* K, const double* RT)
+{
+  const dmi::GridParams& g = ctx->g;
+  const size_t npix = (size_t)g.W * g.H;
+  const size_t tilesPerView = (size_t)dmi::tile_pyramid_layout(g.W, g.H).perView;
+  int chunk = dmi::kFastChunk;
+  if (ctx->opt_chunk > 0 && ctx->opt_chunk < chunk) chunk = (int)ctx->opt_chunk;
+  DMI_CK(ctx->viewscratch.ensure(sizeof(dmi::ViewFast) * dmi::kFastChunk));
+  DMI_CK(ctx->maskscratch.ensure(dmi::tsdf_fast_mask_bytes(g)));
+  dmi::FastChunk* c = &ctx->fast_chunk;
+  dmi::fill_fast_chunk_constants(g, c);
+  for (int v0 = 0; v0 < nViews; v0 += chunk)
+  {
+    c->n = std::min(chunk, nViews - v0);
+    c->pinhole = 1;
+    for (int q = 0; q < c->n; q++)
+    {
+      const double* k16 = K + 16 * (size_t)(v0 + q);
+      const double* rt16 = RT + 16 * (size_t)(v0 + q);
+      dmi::compose_fast_view(g, k16, rt16, c->cxc, c->cyc, &c->v[q]);
+      memcpy(c->e[q].RT, rt16, sizeof(double) * 12);
+      memcpy(c->e[q].K, k16, sizeof(double) * 12);
+      if (!(k16[8] == 0.0 && k16[9] == 0.0 && k16[10] == 1.0 && k16[11] == 0.0)) c->pinhole = 0;
+    }
+    DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths + npix * v0, d_cls + npix * v0, clsSpare - (long long)(npix * (size_t)v0),
+                                 d_tiles + tilesPerView * v0, ctx->opt_cull, (dmi::ViewFast*)ctx->viewscratch.p,
+                                 (unsigned*)ctx->maskscratch.p, ctx->vol.p, ctx->vol_type,
+                                 ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr, ctx->stream));
+    ctx->tsdf_stats.launches++;
+    ctx->total_launches += ctx->opt_cull ? 3 : 2;         // view staging, supertile culling, integration
+  }
+  return DMI_OK;
+}
+
 // Fast kernel over views given as the caller's depth maps + optional best-cost maps (neither modified):
 // the filter is folded into the float classification image built by the view-preparation kernel.
 static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_cost, double thr,
@@ -334,46 +371,22 @@ static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_dep
   const dmi::GridParams& g = ctx->g;
   const size_t npix = (size_t)g.W * g.H;
   const size_t tilesPerView = (size_t)dmi::tile_pyramid_layout(g.W, g.H).perView;
-  int chunk = dmi::kFastChunk;
-  if (ctx->opt_chunk > 0 && ctx->opt_chunk < chunk) chunk = (int)ctx->opt_chunk;
+  const int chunk = dmi::kFastChunk;
   // views prepared at a time: whole chunks, about 1 GB of classification image
   int group = (int)std::max<size_t>(1, (1ull << 30) / (npix * 4));
   group = std::max(chunk, group / chunk * chunk);
   group = std::min(group, (nViews + chunk - 1) / chunk * chunk);
   DMI_CK(ctx->cls.ensure(((size_t)group * npix + 1) * 4));   // + the spare slot holding -1.0f
   DMI_CK(ctx->tiles.ensure((size_t)group * tilesPerView * 4));
-  DMI_CK(ctx->viewscratch.ensure(sizeof(dmi::ViewFast) * dmi::kFastChunk));
-  DMI_CK(ctx->maskscratch.ensure(dmi::tsdf_fast_mask_bytes(g)));
-  dmi::FastChunk* c = &ctx->fast_chunk;
-  dmi::fill_fast_chunk_constants(g, c);
   for (int g0 = 0; g0 < nViews; g0 += group)
   {
     const int gn = std::min(group, nViews - g0);
     DMI_CK(dmi::launch_prepare_views(d_depths + npix * g0, d_cost ? d_cost + npix * g0 : nullptr, thr, gn, g.W, g.H,
-                                     (float*)ctx->cls.p, (float*)ctx->tiles.p, ctx->stream));
+                                     (float*)ctx->cls.p, (long long)(npix * (size_t)gn), (float*)ctx->tiles.p, ctx->stream));
     ctx->total_launches++;
-    for (int v0 = 0; v0 < gn; v0 += chunk)
-    {
-      c->n = std::min(chunk, gn - v0);
-      c->pinhole = 1;
-      for (int q = 0; q < c->n; q++)
-      {
-        const double* k16 = K + 16 * (size_t)(g0 + v0 + q);
-        const double* rt16 = RT + 16 * (size_t)(g0 + v0 + q);
-        dmi::compose_fast_view(g, k16, rt16, c->cxc, c->cyc, &c->v[q]);
-        memcpy(c->e[q].RT, rt16, sizeof(double) * 12);
-        memcpy(c->e[q].K, k16, sizeof(double) * 12);
-        if (!(k16[8] == 0.0 && k16[9] == 0.0 && k16[10] == 1.0 && k16[11] == 0.0)) c->pinhole = 0;
-      }
-      DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths + npix * (g0 + v0), (const float*)ctx->cls.p + npix * v0,
-                                   (long long)(npix * (size_t)(gn - v0)),
-                                   (const float*)ctx->tiles.p + tilesPerView * v0, ctx->opt_cull,
-                                   (dmi::ViewFast*)ctx->viewscratch.p, (unsigned*)ctx->maskscratch.p, ctx->vol.p,
-                                   ctx->vol_type, ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr,
-                                   ctx->stream));
-      ctx->tsdf_stats.launches++;
-      ctx->total_launches += ctx->opt_cull ? 3 : 2;       // view staging, supertile culling, integration
-    }
+    int rc = integrate_fast_prepared(ctx, gn, d_depths + npix * g0, (const float*)ctx->cls.p, (long long)(npix * (size_t)gn),
+                                     (const float*)ctx->tiles.p, K + 16 * (size_t)g0, RT + 16 * (size_t)g0);
+    if (rc != DMI_OK) return rc;
   }
   return DMI_OK;
 }
@@ -428,6 +441,49 @@ int dmi_volume_integrate_device(dmi_ctx* ctx, int nViews, const double* d_depths
   DMI_REQUIRE(d_depths && K && RT, "null argument");
   DMI_CK(cudaSetDevice(ctx->device));
   return integrate_device_views(ctx, nViews, d_depths, d_bestCost, thresholdBestCost, K, RT, false);
+}
+
+int dmi_prepared_view_sizes(dmi_ctx* ctx, size_t* clsFloatsPerView, size_t* tileFloatsPerView)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  if (clsFloatsPerView) *clsFloatsPerView = (size_t)ctx->g.W * ctx->g.H;
+  if (tileFloatsPerView) *tileFloatsPerView = (size_t)dmi::tile_pyramid_layout(ctx->g.W, ctx->g.H).perView;
+  return DMI_OK;
+}
+
+int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
+                             double thresholdBestCost, float* d_cls, long long clsSpareIndex, float* d_tileStats)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
+  DMI_REQUIRE(d_depths && d_cls && d_tileStats, "null argument");
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, d_cls, clsSpareIndex,
+                                   d_tileStats, ctx->stream));
+  ctx->total_launches++;
+  return DMI_OK;
+}
+
+int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const float* d_cls,
+                                  long long clsSpareIndex, const float* d_tileStats, const double* K, const double* RT)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized || !ctx->vol_active) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_volume_begin has not been called");
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
+  DMI_REQUIRE(d_depths && d_cls && d_tileStats && K && RT, "null argument");
+  if (!fast_path_applies(ctx))
+    return ctx->fail(DMI_ERR_BAD_PARAMETERS, "prepared views need the certified fast path (0 < Thick, finite parameters, kernel AUTO)");
+  DMI_CK(cudaSetDevice(ctx->device));
+  if (slab_cells(ctx->g) == 0) return DMI_OK;
+  EventSpan span = ctx->tsdf_stats.open();
+  DMI_CK(cudaEventRecord(span.a, ctx->stream));
+  int rc = integrate_fast_prepared(ctx, nViews, d_depths, d_cls, clsSpareIndex, d_tileStats, K, RT);
+  if (rc != DMI_OK) return rc;
+  DMI_CK(cudaEventRecord(span.b, ctx->stream));
+  ctx->tsdf_stats.pending.push_back(span);
+  return DMI_OK;
 }
 
 int dmi_volume_integrate_host(dmi_ctx* ctx, int nViews, const double* depths, const double* bestCost,

@@ -87,8 +87,9 @@ struct TilePyramid
   int tw[12], th[12], off[12];
 };
 TilePyramid tile_pyramid_layout(int W, int H);
+// clsSpare: index (relative to d_cls) of a float that is set to -1.0f for the rejected voxels' gathers; < 0 = none
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 float* d_cls, float* d_tileDmax, cudaStream_t s);
+                                 float* d_cls, long long clsSpare, float* d_tileDmax, cudaStream_t s);
 // d_cls[clsSpare] (an index relative to d_cls) must hold -1.0f: launch_prepare_views(n views) writes it at n*W*H
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,

@@ -668,9 +668,9 @@ TilePyramid tile_pyramid_layout(int W, int H)
 __global__ void __launch_bounds__(256)
 prepare_views_kernel(const double* __restrict__ depths, const double* __restrict__ cost, double thr,
                      int nViews, int W, int H, int TW, int TH, int perView, float* __restrict__ cls,
-                     float* __restrict__ tileDmax)
+                     long long clsSpare, float* __restrict__ tileDmax)
 {
-  if (blockIdx.x == 0 && threadIdx.x == 0) cls[(size_t)nViews * W * H] = -1.0f;   // the spare slot, see phase B
+  if (blockIdx.x == 0 && threadIdx.x == 0 && clsSpare >= 0) cls[clsSpare] = -1.0f;   // the spare slot, see phase B
   const int lane = threadIdx.x & 31;
   const size_t tile = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t tilesPerView = (size_t)TW * TH;
@@ -726,13 +726,13 @@ tile_pyramid_kernel(float* __restrict__ tiles, int nViews, int perView, int offS
 }
 
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 float* d_cls, float* d_tileDmax, cudaStream_t s)
+                                 float* d_cls, long long clsSpare, float* d_tileDmax, cudaStream_t s)
 {
   const TilePyramid p = tile_pyramid_layout(W, H);
   const size_t tiles = (size_t)p.tw[0] * p.th[0] * nViews;
   if (tiles == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((tiles + 7) / 8);
-  prepare_views_kernel<<<blocks, 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw[0], p.th[0], p.perView, d_cls, d_tileDmax);
+  prepare_views_kernel<<<blocks, 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw[0], p.th[0], p.perView, d_cls, clsSpare, d_tileDmax);
   for (int l = 1; l < p.nLevels; l++)
   {
     const size_t n = (size_t)p.tw[l] * p.th[l] * nViews;

@@ -149,6 +149,22 @@ class Context:
                                                        _ptr(int(d_best_cost)) if d_best_cost else None,
                                                        float(threshold_best_cost), _ptr(K), _ptr(RT)))
 
+    def prepared_view_sizes(self):
+        a, b = C.c_size_t(), C.c_size_t()
+        self._ck(self._lib.dmi_prepared_view_sizes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def prepare_views_device(self, n_views: int, d_depths: int, d_best_cost: int | None, threshold, d_cls: int,
+                             cls_spare_index: int, d_tiles: int):
+        self._ck(self._lib.dmi_prepare_views_device(self._h, int(n_views), _ptr(int(d_depths)),
+                                                    _ptr(int(d_best_cost)) if d_best_cost else None, float(threshold),
+                                                    _ptr(int(d_cls)), int(cls_spare_index), _ptr(int(d_tiles))))
+
+    def volume_integrate_prepared(self, n_views: int, d_depths: int, d_cls: int, cls_spare_index: int, d_tiles: int, K, RT):
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        self._ck(self._lib.dmi_volume_integrate_prepared(self._h, int(n_views), _ptr(int(d_depths)), _ptr(int(d_cls)),
+                                                         int(cls_spare_index), _ptr(int(d_tiles)), _ptr(K), _ptr(RT)))
+
     def volume_end(self, h_scalar: np.ndarray | None = None):
         if h_scalar is not None and (h_scalar.size != self.slab_cells or h_scalar.dtype != self._vol_dtype):
             raise ValueError("h_scalar must match the slab's size and scalar type")

@@ -338,3 +338,34 @@ def test_full_size_properties_512_cube_1080p(gpu_ctx):
     # just inside the surface along +x: positive (behind the surface within Thick)
     r_in = int(n / 2 + (1.0 - 1.5 * float(grid.spacing[0])) / float(grid.spacing[0]))
     assert vol[n // 2, n // 2, r_in].item() > 0
+
+
+def test_prepared_views_path_is_bit_identical(gpu_ctx):
+    """dmi_prepare_views_device + dmi_volume_integrate_prepared (the multi-GPU split: owners prepare, everyone
+    integrates) == dmi_volume_integrate_device, bit for bit, also when the views are prepared in two pieces."""
+    import torch
+    n, nv, W, H = 96, 20, 320, 240
+    grid, rp, K, RT, d, c = _device_scene(n, nv, W, H)
+    whole = _integrate_device(gpu_ctx, grid, rp, K, RT, d, c, W, H)
+    ctx = gpu_ctx
+    ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_AUTO)
+    ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
+    ncls, ntile = ctx.prepared_view_sizes()
+    assert ncls == W * H
+    cls = torch.empty(nv * ncls + 1, dtype=torch.float32, device=d.device)
+    tiles = torch.empty(nv * ntile, dtype=torch.float32, device=d.device)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        npix = W * H
+        # two "owners": views [0,8) and [8,20); only the second call writes the spare slot
+        ctx.prepare_views_device(8, d.data_ptr(), c.data_ptr(), 0.14, cls.data_ptr(), -1, tiles.data_ptr())
+        ctx.prepare_views_device(12, d.data_ptr() + 8 * npix * 8, c.data_ptr() + 8 * npix * 8, 0.14,
+                                 cls.data_ptr() + 8 * npix * 4, 12 * npix, tiles.data_ptr() + 8 * ntile * 4)
+        ctx.volume_begin(None, np.float64)
+        ctx.volume_integrate_prepared(nv, d.data_ptr(), cls.data_ptr(), nv * npix, tiles.data_ptr(), K, RT)
+        out = np.empty(n ** 3)
+        ctx.volume_end(out)
+    finally:
+        ctx.set_stream(None)
+    assert cls[-1].item() == -1.0
+    assert np.array_equal(out, whole.cpu().numpy())
