@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
                     help="N=1 diagnostic: integrate only the z-slab that RANK of WORLD would own (value counts that slab's pairs)")
     ap.add_argument("--breakdown", action="store_true", help="N>1: print the comm / compute / gather spans of the last step to stderr")
+    ap.add_argument("--cost-model", default="iid", choices=["iid", "coherent"],
+                    help="synthetic best-cost maps: independent per pixel (default, the headline workload) or spatially coherent")
     ap.add_argument("--color-points", type=int, default=2000000)
     ap.add_argument("--color-views", type=int, default=200)
     return ap.parse_args()
@@ -185,7 +187,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "voxel*views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -255,7 +257,27 @@ def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+_JSON_OUT = None
+
+
+def emit(text):
+    """The ONE JSON line goes to the real stdout; everything else a library prints to fd 1 (NCCL's version
+    banner, for instance) has been redirected to stderr by guard_stdout()."""
+    if _JSON_OUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_JSON_OUT, (text + "\n").encode())
+
+
+def guard_stdout():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    guard_stdout()
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -343,7 +365,8 @@ def main():
         runs = np.split(idx, np.where(np.diff(idx) != 1)[0] + 1)     # render_views hashes on first_view + offset
         off = s0
         for r in runs:
-            d, c, _ = syn.render_views(K[r], RT[r], W, H, first_view=int(r[0]), device=dev, depth_noise=noise, want_color=False)
+            d, c, _ = syn.render_views(K[r], RT[r], W, H, first_view=int(r[0]), device=dev, depth_noise=noise, want_color=False,
+                                        cost_model=args.cost_model)
             my_depths[off:off + len(r)] = d
             my_cost[off:off + len(r)] = c
             off += len(r)
@@ -526,18 +549,19 @@ def main():
         all_pairs_tflops = FLOPS_PER_UNIT * k_units / k_sec / 1e12
         evaluated = 1.0
         if tiers and tiers["brick_views"] > 0:
-            evaluated = 1.0 - tiers["culled_brick_views"] / tiers["brick_views"]
+            evaluated = 1.0 - (tiers["culled_brick_views"] + tiers["uniform_front"]) / tiers["brick_views"]
         ach = all_pairs_tflops * evaluated
         alg_bytes = algorithmic_bytes(N, V, W, H) / world * args.steps
         roofline = {
             "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
             "traffic": None,
             "kernel": "tsdf_fast_kernel" if args.kernel != "exact" else "tsdf_exact_kernel",
-            "definition": "28 algorithmic flops x the voxel*view pairs the kernel EVALUATED (pairs culled by the exact brick tests "
-                          "are excluded) / summed CUDA-event time of the integration launches of the timed region",
+            "definition": "28 algorithmic flops x the voxel*view pairs the kernel EVALUATED one by one (pairs settled by the exact "
+                          "brick tests -- culled, or free space in front of the surface: one add -- are excluded) / summed CUDA-event time of the integration launches of the timed region",
             "peak_source": "FFMA issue-rate microbenchmark run in this process (dmi_measure_fp_peak); MEASURED_PEAKS.json has no FP32/FP64 vector peak",
             "binding_resource": "instruction issue (compares, rounding, address arithmetic, one gather per pair): see profiles/ for smsp__issue_active",
             "evaluated_fraction_of_pairs": evaluated,
+            "free_space_fraction_of_pairs": (tiers["uniform_front"] / tiers["brick_views"]) if tiers and tiers["brick_views"] else None,
             "all_pairs": {"achieved": all_pairs_tflops, "frac_fp32": all_pairs_tflops / fp32_peak, "frac_fp64": all_pairs_tflops / fp64_peak,
                           "note": "all N^3*V pairs counted as SURVEY.md 8d asks; exceeds the FMA roofline because most pairs are proven to contribute nothing without being evaluated"},
             "fp64_basis": {"peak": fp64_peak, "frac": ach / fp64_peak, "peak_source": "DFMA microbenchmark, this process"},
@@ -558,7 +582,7 @@ def main():
             "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H}, best-cost threshold {THRESH}, f64 volume",
                        "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views exchanged in groups of {G} ({'copy-engine pushes over CUDA IPC' if args.exchange == 'ce' else 'NCCL all-gather'})" if world > 1 else ""),
                        "l2": "inputs (%.1f GB per step) exceed L2; no flush needed" % (algorithmic_bytes(N, V, W, H) / 1e9),
-                       "kernel": args.kernel, "cull": args.cull},
+                       "kernel": args.kernel, "cull": args.cull, "cost_model": args.cost_model},
             "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
             "volume_digest": digest,
         }
@@ -569,7 +593,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             rate, desc, _ = cpu_reference_rate(N, V, W, H, target_seconds=12.0)
             line["cpu_baseline"] = dict(desc, value=rate, unit="voxel*views/s")
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -597,10 +621,14 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
         vol_np, d_np, c_np = h_vol.numpy(), h_depths.numpy(), h_cost.numpy()
 
         def step():
-            vol_np.fill(0.0)      # the filter zero-fills its output before the call (vtkCudaReconstructionFilter.cxx:133)
-            ctx.process_depth_maps(d_np, c_np, THRESH, K, RT, vol_np)
-        api = "dmi_process_depth_maps (host pointers; pinned host buffers; includes the upload of io_scalar the reference also does)"
-        h2d = int(2 * nmine * npix * 8 + slab_cells * 8)
+            # what the filter's RequestData does (vtkCudaReconstructionFilter.cxx:133-147), as DmiHostClasses.h /
+            # reconstruction.py do it: the zero fill of the output happens on the device, the views stream in
+            # from host memory, the finished cell scalars are read back into the host array
+            ctx.volume_begin(None, np.float64)
+            ctx.volume_integrate_host(d_np, c_np, THRESH, K, RT)
+            ctx.volume_end(vol_np)
+        api = "dmi_volume_begin(NULL) + dmi_volume_integrate_host + dmi_volume_end (host pointers; pinned host buffers)"
+        h2d = int(2 * nmine * npix * 8)
     else:
         def step():
             my_depths.copy_(h_depths, non_blocking=True)
@@ -612,7 +640,17 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
     step()
     ms, wall = timed(step, steps)
     sec = max(ms, wall) * 1e-3
-    return {"value": units / sec, "unit": "voxel*views/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": 1,
+    extra = {}
+    if world == 1:
+        # the one-call entry with an io_scalar the caller zero-filled on the host (the reference's calling sequence)
+        t0 = time.perf_counter()
+        vol_np.fill(0.0)
+        t1 = time.perf_counter()
+        ctx.process_depth_maps(d_np, c_np, THRESH, K, RT, vol_np)
+        t2 = time.perf_counter()
+        extra["via_process_depth_maps"] = {"host_zero_fill_ms": (t1 - t0) * 1e3, "call_ms": (t2 - t1) * 1e3,
+                                           "note": "io_scalar zero-filled by the caller; the library verifies that on the host instead of uploading it"}
+    return {**extra, "value": units / sec, "unit": "voxel*views/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": 1,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(slab_cells * 8), "bytes_are": "per rank", "api": api}
 
 

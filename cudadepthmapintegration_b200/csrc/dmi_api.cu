@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 namespace {
 
@@ -272,7 +274,62 @@ static size_t slab_cells(const dmi::GridParams& g)
   return (size_t)g.Nx * g.Ny * (size_t)(g.k1 - g.k0);
 }
 
+// True when every BIT of the host array is zero (-0.0 is not: s + t keeps its sign when nothing is added).
+// The reference's filter zero-fills its output before the call (vtkCudaReconstructionFilter.cxx:133), so
+// the usual io_scalar needs no upload: a parallel scan at memory speed is several times cheaper than PCIe.
+static bool host_bytes_all_zero(const void* p, size_t bytes)
+{
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  size_t head = 0;
+  while (head < bytes && (reinterpret_cast<uintptr_t>(b + head) & 7)) { if (b[head]) return false; head++; }
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(b + head);
+  const size_t words = (bytes - head) / 8;
+  for (size_t q = head + words * 8; q < bytes; q++) if (b[q]) return false;
+  const size_t block = 1u << 17;                                   // 1 MB of words between looks at the flag
+  unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  if (words < (size_t)nt * block) nt = 1;
+  std::atomic<bool> nonzero(false);
+  auto scan = [&](size_t w0, size_t w1) {
+    for (size_t q = w0; q < w1 && !nonzero.load(std::memory_order_relaxed); q += block)
+    {
+      unsigned long long acc = 0;
+      const size_t e = std::min(w1, q + block);
+      for (size_t r = q; r < e; r++) acc |= w[r];
+      if (acc) nonzero.store(true, std::memory_order_relaxed);
+    }
+  };
+  if (nt == 1) scan(0, words);
+  else
+  {
+    std::vector<std::thread> th;
+    const size_t per = (words + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(scan, std::min(words, t * per), std::min(words, (t + 1) * per));
+    for (auto& t : th) t.join();
+  }
+  return !nonzero.load();
+}
+
+// Cheap necessary condition for "all zero": both ends and 4096 words spread over the array.
+static bool host_zero_probe(const void* p, size_t bytes)
+{
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  const size_t edge = std::min<size_t>(bytes, 65536);
+  for (size_t q = 0; q < edge; q++) if (b[q] | b[bytes - 1 - q]) return false;
+  const size_t stride = std::max<size_t>(1, bytes / 4096);
+  for (size_t q = 0; q < bytes; q += stride) if (b[q]) return false;
+  return true;
+}
+
+enum VolumeInit { kVolScan = 0, kVolUpload = 1, kVolAssumeZero = 2 };
+
+static int volume_begin_impl(dmi_ctx* ctx, const void* h_scalar, int scalarType, VolumeInit mode);
+
 int dmi_volume_begin(dmi_ctx* ctx, const void* h_scalar, int scalarType)
+{
+  return volume_begin_impl(ctx, h_scalar, scalarType, kVolScan);
+}
+
+static int volume_begin_impl(dmi_ctx* ctx, const void* h_scalar, int scalarType, VolumeInit mode)
 {
   if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
   if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
@@ -284,7 +341,10 @@ int dmi_volume_begin(dmi_ctx* ctx, const void* h_scalar, int scalarType)
   ctx->vol_type = scalarType;
   if (bytes)
   {
-    if (h_scalar) DMI_CK(cudaMemcpyAsync(ctx->vol.p, h_scalar, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const bool upload = h_scalar && (mode == kVolUpload ||
+                                     (mode == kVolScan && !(host_zero_probe(h_scalar, bytes) && host_bytes_all_zero(h_scalar, bytes))));
+    if (upload)
+      DMI_CK(cudaMemcpyAsync(ctx->vol.p, h_scalar, bytes, cudaMemcpyHostToDevice, ctx->stream));
     else DMI_CK(cudaMemsetAsync(ctx->vol.p, 0, bytes, ctx->stream));
   }
   ctx->vol_active = true;
@@ -551,10 +611,25 @@ int dmi_process_depth_maps(dmi_ctx* ctx, int nViews, const double* depths, const
   if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
   if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
   DMI_REQUIRE(depths && K && RT && io_scalar, "null argument");
-  int rc = dmi_volume_begin(ctx, io_scalar, scalarType);
+  DMI_REQUIRE(scalarType == DMI_F32 || scalarType == DMI_F64, "scalarType must be DMI_F32 or DMI_F64");
+  // A large io_scalar that looks all-zero (the filter zero-fills it, vtkCudaReconstructionFilter.cxx:133) is
+  // verified by a full host scan WHILE the views stream in and integrate onto a zeroed device volume; should
+  // the scan find a set bit after all, the pass is repeated from the uploaded io_scalar (inputs are still here).
+  const size_t bytes = slab_cells(ctx->g) * (scalarType == DMI_F64 ? 8 : 4);
+  const bool speculate = bytes >= (256u << 20) && host_zero_probe(io_scalar, bytes);
+  bool zero = true;
+  std::thread scan;
+  if (speculate) scan = std::thread([&] { zero = host_bytes_all_zero(io_scalar, bytes); });
+  int rc = volume_begin_impl(ctx, io_scalar, scalarType, speculate ? kVolAssumeZero : kVolScan);
+  if (rc == DMI_OK) rc = dmi_volume_integrate_host(ctx, nViews, depths, bestCost, thresholdBestCost, K, RT);
+  if (speculate) scan.join();
   if (rc != DMI_OK) return rc;
-  rc = dmi_volume_integrate_host(ctx, nViews, depths, bestCost, thresholdBestCost, K, RT);
-  if (rc != DMI_OK) return rc;
+  if (speculate && !zero)
+  {
+    rc = volume_begin_impl(ctx, io_scalar, scalarType, kVolUpload);
+    if (rc == DMI_OK) rc = dmi_volume_integrate_host(ctx, nViews, depths, bestCost, thresholdBestCost, K, RT);
+    if (rc != DMI_OK) return rc;
+  }
   return dmi_volume_end(ctx, io_scalar);
 }
 
@@ -580,7 +655,7 @@ int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches)
   return DMI_OK;
 }
 
-int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[8])
+int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[16])
 {
   if (!ctx || !out) return DMI_ERR_INVALID_ARGUMENT;
   if (!ctx->counters_on) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "enable DMI_OPT_TIER_COUNTERS first");

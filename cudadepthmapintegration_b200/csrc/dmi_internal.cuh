@@ -71,20 +71,28 @@ struct FastChunk
 struct FastCounters               // optional diagnostics (device memory, may be null)
 {
   unsigned long long t1_certified, t2_entered, t3_entered, delta_guard, units, culled, near_band, brick_views;
+  unsigned long long uniform_front;     // (brick, view) pairs settled by one add per voxel, see eval_box
+  unsigned long long reserved[7];
 };
 
 // Per-view data the fast kernel gathers from, built by launch_prepare_views:
 //   cls       float[n][H][W]   depth rounded to float, -1.0f exactly on the pixels that are invalid after
 //                              the best-cost filter (never -1.0f on a valid pixel)
-//   tileDmax  float[n][TH][TW] per 16x16 tile of storage rows: max valid depth (rounded up), -inf when the
-//                              tile has no valid pixel, +inf when it holds a NaN
-// The tile statistics form a max-pyramid per view: level l has tiles of 16 * 2^l pixels, so that a brick
-// footprint of any size is covered by at most 2 x 2 tiles of the right level.
+//   tileStats float[n][perView] per 8x8 tile of storage rows: max valid depth (rounded up), -inf when the
+//                              tile has no valid pixel, +inf when it holds a NaN; and, minOff floats further,
+//                              min depth (rounded down) when EVERY pixel of the tile inside the image is valid
+//                              and not NaN, -inf otherwise
+// The statistics form a sparse table per view: level l holds, AT EVERY TILE POSITION (x, y), the statistic
+// of the window of 2^l x 2^l tiles whose corner is (x, y) (clipped by the image).  Any rectangle of tiles is
+// the union of four overlapping windows of level floor(log2(longer side)): exact along the longer side,
+// at most 2x over-covered along the shorter one -- tight bounds for a brick footprint of any size in 4 loads.
 struct TilePyramid
 {
   int nLevels;
-  int perView;                    // floats per view, all levels
-  int tw[12], th[12], off[12];
+  int tw, th;                     // tiles per row / column; every level has tw * th entries
+  int perView;                    // floats per view: both tables + the flag
+  int minOff;                     // the min table starts here; level l of either table at l * tw * th
+  int flagOff;                    // one float: 1.0f when some tile of the view is fully valid
 };
 TilePyramid tile_pyramid_layout(int W, int H);
 // clsSpare: index (relative to d_cls) of a float that is set to -1.0f for the rejected voxels' gathers; < 0 = none

@@ -87,7 +87,7 @@ private:
     const int dd[2] = {img.W, img.H};
     if (dmi_initialize(ctx_, GridMatrix, Dims, Origin, Spacing, RayPotentialThickness, RayPotentialRho,
                        RayPotentialEta, RayPotentialDelta, dd) != DMI_OK ||
-        dmi_volume_begin(ctx_, Output.data(), DMI_F64) != DMI_OK)
+        dmi_volume_begin(ctx_, nullptr, DMI_F64) != DMI_OK)      // Output was just zero-filled: nothing to upload
     { std::cerr << dmi_last_error(ctx_) << std::endl; return -1; }
     const size_t npix = (size_t)img.W * img.H;
     const size_t batch = std::max<size_t>(1, std::min<size_t>(32, (256u << 20) / (npix * 8)));

@@ -40,7 +40,7 @@ constexpr int FT = 128;
 constexpr int FSI = 4, FSJ = 4, FSK = 4;    // supertile = 64 x 32 x 32 voxels, enumerated contiguously
 constexpr float kMagic = 12582912.0f;       // 1.5 * 2^23: adding it rounds |x| < 2^22 to an integer
 constexpr int kMagicBits = 0x4B400000;
-constexpr int kTile = 16;                   // tile edge of the per-view tile statistics
+constexpr int kTile = 8;                    // tile edge of the per-view tile statistics
 
 constexpr int kBad = INT_MIN + 2;           // every valid gather index (px - py*W) is above this
 constexpr int kReject = kBad - 1;           // certified: this voxel*view contributes nothing
@@ -151,7 +151,7 @@ struct __align__(16) ViewSm
   int pad;
 };
 
-struct BrickBox { bool valid; float ux, uy; int tx0, tx1, ty0, ty1; };
+struct BrickBox { bool valid, inside; float ux, uy; int tx0, tx1, ty0, ty1; };
 
 // Projected bounding box of a box of voxels for one view (8 corners; the projection of a box with hz > 0
 // is the convex hull of its projected corners).  (ei, ej, ek) = extents - 1 in voxels; (lx, ly, lz) bound
@@ -186,6 +186,7 @@ __device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c,
   o.uy = fmaxf(fabsf(vlo), fabsf(vhi));
   const float xlo = ulo + (float)c.cxc, xhi = uhi + (float)c.cxc, ylo = vlo + (float)c.cyc, yhi = vhi + (float)c.cyc;
   if (!(xhi >= 0.f && xlo <= (float)(W - 1) && yhi >= 0.f && ylo <= (float)(H - 1))) { outside = true; return true; }
+  o.inside = xlo >= 0.f && xhi <= (float)(W - 1) && ylo >= 0.f && yhi <= (float)(H - 1);   // every voxel lands in the image
   const int px0 = max(0, (int)floorf(xlo)), px1 = min(W - 1, (int)ceilf(xhi));
   const int py0 = max(0, (int)floorf(ylo)), py1 = min(H - 1, (int)ceilf(yhi));
   // pixel bounds in STORAGE coordinates (rows are bottom-up: row = H-1-py)
@@ -194,28 +195,30 @@ __device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c,
   return true;
 }
 
-// Max of the valid depths over a pixel rectangle (storage coordinates), read from the pyramid level whose
-// tiles are at least as large as the rectangle: at most 2 x 2 tiles, all four loads in flight together.
-__device__ __forceinline__ float footprint_dmax(const TilePyramid& pyr, const float* __restrict__ td, const BrickBox& b)
+// Max (or all-valid min) of the depths over a pixel rectangle (storage coordinates) from the view's sparse
+// table: four overlapping windows of 2^l x 2^l tiles, l = floor(log2(longer side in tiles)); all four loads
+// are in flight together.
+template <bool MIN>
+__device__ __forceinline__ float footprint_stat(const TilePyramid& pyr, const float* __restrict__ td, const BrickBox& b)
 {
-  const int e = max(b.tx1 - b.tx0, b.ty1 - b.ty0);            // extent - 1
-  const int q = e >> 4;
-  const int L = min(q == 0 ? 0 : 32 - __clz(q), pyr.nLevels - 1);
-  const int sh = 4 + L;
-  const int tw = pyr.tw[L], th = pyr.th[L];
-  const int x0 = b.tx0 >> sh, x1 = min(b.tx1 >> sh, tw - 1), y0 = b.ty0 >> sh, y1 = min(b.ty1 >> sh, th - 1);
-  const float* t = td + pyr.off[L];
-  // beyond 2 x 2 only on the coarsest level, which is a single tile
-  const float a = __ldg(t + y0 * tw + x0), bq = __ldg(t + y0 * tw + x1);
-  const float cq = __ldg(t + y1 * tw + x0), dq = __ldg(t + y1 * tw + x1);
-  return fmaxf(fmaxf(a, bq), fmaxf(cq, dq));
+  const int X0 = b.tx0 >> 3, X1 = min(b.tx1 >> 3, pyr.tw - 1), Y0 = b.ty0 >> 3, Y1 = min(b.ty1 >> 3, pyr.th - 1);
+  const int n = max(X1 - X0, Y1 - Y0) + 1;
+  const int l = min(31 - __clz(n), pyr.nLevels - 1);          // nLevels covers every n <= max(tw, th)
+  const int sdim = 1 << l;
+  const int xb = max(X0, X1 - sdim + 1), yb = max(Y0, Y1 - sdim + 1);
+  const float* t = td + (size_t)l * (pyr.tw * pyr.th) + (MIN ? pyr.minOff : 0);
+  const float a = __ldg(t + Y0 * pyr.tw + X0), bq = __ldg(t + Y0 * pyr.tw + xb);
+  const float cq = __ldg(t + yb * pyr.tw + X0), dq = __ldg(t + yb * pyr.tw + xb);
+  return MIN ? fminf(fminf(a, bq), fminf(cq, dq)) : fmaxf(fmaxf(a, bq), fmaxf(cq, dq));
 }
 
 // Everything the pre-pass needs to know about (box of voxels, view): FP64 base of the rows at the box
 // origin rounded to float, |u| bounds over the box, and whether the view can be CULLED for the whole box:
 // every voxel behind the camera (:177), outside the image (:192-197), over tiles without a valid pixel
 // (:202), or farther than Delta BEHIND every valid depth it can meet (rayPotential returns 0, :114-115).
-struct BoxEval { bool keep; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs; };
+// `front`: every voxel of the box lands inside the image on a valid pixel and is farther than Delta IN FRONT
+// of every depth it can meet: the view adds exactly -Eta*Rho to every voxel (:114-115), no projection needed.
+struct BoxEval { bool keep, front; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs; };
 
 template <bool PINHOLE>
 __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& c, const TilePyramid& pyr,
@@ -244,7 +247,8 @@ __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& 
   }
   o.czmaxabs = fmaxf(fabsf(clo), fabsf(chi));
   o.keep = true;
-  BrickBox box; box.valid = false;
+  o.front = false;
+  BrickBox box; box.valid = false; box.inside = false;
   bool outside = false;
   const bool boxed = brick_box(V, c, o.fbx, o.fby, o.fbz, ei, ej, ek, lx, ly, lz, zlo, W, H, box, outside);
   if (boxed) { o.Ux = fminf(c.umax1g, box.ux + 1.f); o.Uy = fminf(c.umax1g, box.uy + 1.f); }
@@ -254,9 +258,10 @@ __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& 
     else if (boxed && outside) o.keep = false;
     else if (boxed && box.valid)
     {
-      const float dmax = footprint_dmax(pyr, td, box);
+      const float dmax = footprint_stat<false>(pyr, td, box);
       const float thr = c.delta_up + 1e-6f * o.czmaxabs;
       if (dmax == -INFINITY || clo - dmax > thr) o.keep = false;
+      else if (box.inside && V.pad[0] != 0.f && footprint_stat<true>(pyr, td, box) - chi > thr) o.front = true;
     }
   }
   return o;
@@ -347,6 +352,7 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
       int pos = __popc(bal & ((1u << lane) - 1u));
       for (int q = 0; q < w; q++) pos += s_cnt[q];
       ViewSm& S = s_view[pos];
+      S.pad = e.front ? 1 : 0;
       const float Ex = c.k3 * ((fabsf(e.fbx) + 3.f * V.lx) + e.Ux * (fabsf(e.fbz) + 3.f * V.lz));
       const float Ey = c.k3 * ((fabsf(e.fby) + 3.f * V.ly) + e.Uy * (fabsf(e.fbz) + 3.f * V.lz));
       S.base = make_float4(e.fbx, e.fby, e.fbz, V.zm);
@@ -363,13 +369,24 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   int nsurv = 0;
 #pragma unroll
   for (int q = 0; q < FT / 32; q++) nsurv += s_cnt[q];
+  if (nsurv == 0)
+  {
+    if (COUNT && counters && threadIdx.x == 0)
+    {
+      atomicAdd(&counters->culled, (unsigned long long)c.n);
+      atomicAdd(&counters->brick_views, (unsigned long long)c.n);
+    }
+    return;                                                   // the brick's voxels are not even read
+  }
+  __syncthreads();
   if (COUNT && counters && threadIdx.x == 0)
   {
+    int nf = 0;
+    for (int q = 0; q < nsurv; q++) nf += s_view[q].pad;
     atomicAdd(&counters->culled, (unsigned long long)(c.n - nsurv));
     atomicAdd(&counters->brick_views, (unsigned long long)c.n);
+    atomicAdd(&counters->uniform_front, (unsigned long long)nf);
   }
-  if (nsurv == 0) return;                                     // the brick's voxels are not even read
-  __syncthreads();
 
   const int li = (w & 1) * 8 + (lane & 7), lj = (w >> 1) * 4 + (lane >> 3);
   const int i = i0 + li, j = j0 + lj;
@@ -390,11 +407,18 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   const int negW = -W;
   const double delta = g.delta, thick = g.thick;
   const T nerT = (T)g.neg_eta_rho;
-  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0;
+  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0, n_uf = 0;
 
   for (int q = 0; q < nsurv; q++)
   {
     const ViewSm& S = s_view[q];
+    if (S.pad)                                                // CTA-uniform: the whole brick is free space for this view
+    {
+#pragma unroll
+      for (int m = 0; m < FM; m++) acc[m] = add_rn(acc[m], nerT);
+      if (COUNT) n_uf++;
+      continue;
+    }
     const float4 b = S.base, et = S.et, cx = S.cx, cy = S.cy, cz = S.cz;
     const int v = S.view;
     // one rounding at base magnitude here, one in the per-voxel FFMA (delta_n = 3 * 2^-24 * ...)
@@ -562,7 +586,7 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   {
     // one atomic per warp and counter (the lanes that returned early above are simply absent)
     const unsigned act = __activemask();
-    unsigned long long vals[6] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)FM * nsurv};
+    unsigned long long vals[6] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)FM * (nsurv - n_uf)};
 #pragma unroll
     for (int q = 0; q < 6; q++)
     {
@@ -586,12 +610,17 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   }
 }
 
-__global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant__ FastChunk c, ViewFast* __restrict__ dst)
+// pad[0] of each staged view = the view's "has a fully valid tile" flag from its tile statistics: views
+// without one (salt-and-pepper holes) skip the free-space test of eval_box altogether.
+__global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant__ FastChunk c, ViewFast* __restrict__ dst,
+                                                          const float* __restrict__ tiles, int perView, int flagOff)
 {
   const unsigned* src = reinterpret_cast<const unsigned*>(c.v);
   unsigned* d = reinterpret_cast<unsigned*>(dst);
   const int words = (int)(sizeof(ViewFast) / 4) * c.n;
   for (int q = threadIdx.x; q < words; q += blockDim.x) d[q] = src[q];
+  __syncthreads();
+  if ((int)threadIdx.x < c.n) dst[threadIdx.x].pad[0] = tiles[(size_t)threadIdx.x * perView + flagOff];
 }
 
 template <typename T, bool PINHOLE>
@@ -630,7 +659,7 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
   const unsigned grid = nsi * nsj * nsk * (FSI * FSJ * FSK);
   const TilePyramid pyr = tile_pyramid_layout(g.W, g.H);
   // stream-ordered copy of the views from the parameter space to global memory, for the pre-pass
-  stage_views_kernel<<<1, 256, 0, s>>>(c, d_viewScratch);
+  stage_views_kernel<<<1, 256, 0, s>>>(c, d_viewScratch, d_tileDmax, pyr.perView, pyr.flagOff);
   const ViewFast* d_views = d_viewScratch;
   if (scalarType == 1)
   {
@@ -646,40 +675,39 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
 }
 
 // ---- view preparation: best-cost filter (ReconstructionData.cxx:159-166) folded into a float
-// classification image, plus the tile max-pyramid for the brick culling.  Level 0: one warp per 16x16
-// tile of storage rows, each lane 8 consecutive pixels; a single HBM-bound pass over the maps.
+// classification image, plus the sparse tables of tile statistics for the brick tests.  Level 0: one warp
+// per 16 x 16 pixels of storage rows (2 x 2 tiles), each lane 8 consecutive pixels; a single HBM-bound pass
+// over the maps.
 TilePyramid tile_pyramid_layout(int W, int H)
 {
   TilePyramid p;
-  int tw = (W + kTile - 1) / kTile, th = (H + kTile - 1) / kTile, off = 0, l = 0;
-  for (;; l++)
-  {
-    p.tw[l] = tw; p.th[l] = th; p.off[l] = off;
-    off += tw * th;
-    if ((tw == 1 && th == 1) || l == 11) break;
-    tw = (tw + 1) / 2; th = (th + 1) / 2;
-  }
+  p.tw = (W + kTile - 1) / kTile;
+  p.th = (H + kTile - 1) / kTile;
+  int m = std::max(std::max(p.tw, p.th), 1), l = 0;
+  while ((2 << l) <= m) l++;                                  // floor(log2(m))
   p.nLevels = l + 1;
-  for (int q = p.nLevels; q < 12; q++) { p.tw[q] = 1; p.th[q] = 1; p.off[q] = p.off[p.nLevels - 1]; }
-  p.perView = off;
+  p.minOff = p.nLevels * p.tw * p.th;
+  p.flagOff = 2 * p.minOff;
+  p.perView = p.flagOff + 4;
   return p;
 }
 
 __global__ void __launch_bounds__(256)
 prepare_views_kernel(const double* __restrict__ depths, const double* __restrict__ cost, double thr,
-                     int nViews, int W, int H, int TW, int TH, int perView, float* __restrict__ cls,
-                     long long clsSpare, float* __restrict__ tileDmax)
+                     int nViews, int W, int H, int TW, int TH, int perView, int minOff, float* __restrict__ cls,
+                     long long clsSpare, float* __restrict__ tileStats)
 {
   if (blockIdx.x == 0 && threadIdx.x == 0 && clsSpare >= 0) cls[clsSpare] = -1.0f;   // the spare slot, see phase B
   const int lane = threadIdx.x & 31;
-  const size_t tile = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t tilesPerView = (size_t)TW * TH;
-  if (tile >= tilesPerView * nViews) return;
-  const int v = (int)(tile / tilesPerView);
-  const int t = (int)(tile % tilesPerView);
-  const int ty = t / TW, tx = t % TW;
-  const int row = ty * kTile + (lane >> 1), col = tx * kTile + (lane & 1) * 8;
-  float dmax = -INFINITY;
+  const int BW = (TW + 1) / 2, BH = (TH + 1) / 2;             // blocks of 2 x 2 tiles
+  const size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t blocksPerView = (size_t)BW * BH;
+  if (blk >= blocksPerView * nViews) return;
+  const int v = (int)(blk / blocksPerView);
+  const int t = (int)(blk % blocksPerView);
+  const int by = t / BW, bx = t % BW;
+  const int row = by * 16 + (lane >> 1), col = bx * 16 + (lane & 1) * 8;
+  float dmax = -INFINITY, dmin = INFINITY;
   if (row < H)
   {
     const size_t base = (size_t)v * W * H + (size_t)row * W;
@@ -699,46 +727,71 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
           float up = f;
           if ((double)up < d) up = __int_as_float(__float_as_int(up) + (up >= 0.f ? 1 : -1));
           dmax = (d != d) ? INFINITY : fmaxf(dmax, up);
+          // tile minimum, rounded down; NaN or an invalid pixel poisons it (-inf: never "free space")
+          float dn = f;
+          if ((double)dn > d) dn = __int_as_float(__float_as_int(dn) + (dn > 0.f ? -1 : 1));
+          dmin = (d != d) ? -INFINITY : fminf(dmin, dn);
         }
+        else dmin = -INFINITY;
         cls[base + col + q] = f;
       }
     }
   }
+  // the 8 lanes of a tile: same column half (bit 0) and same row half (bit 4)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-  if (lane == 0) tileDmax[(size_t)v * perView + t] = dmax;
+  for (int o = 2; o <= 8; o <<= 1)
+  {
+    dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+  }
+  const int tx = bx * 2 + (lane & 1), ty = by * 2 + (lane >> 4);
+  if ((lane & 14) == 0 && tx < TW && ty < TH)
+  {
+    float* o = tileStats + (size_t)v * perView + ty * TW + tx;
+    o[0] = dmax;
+    o[minOff] = dmin;
+  }
 }
 
-// level l from level l-1: max over the (up to) 2 x 2 children
+// level l from level l-1: windows of 2^l tiles = four windows of 2^(l-1) tiles, h = 2^(l-1) apart (clipped)
 __global__ void __launch_bounds__(256)
-tile_pyramid_kernel(float* __restrict__ tiles, int nViews, int perView, int offSrc, int twS, int thS,
-                    int offDst, int twD, int thD)
+tile_level_kernel(float* __restrict__ tiles, int nViews, int perView, int minOff, int tw, int th, int l)
 {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t per = (size_t)twD * thD;
+  const size_t per = (size_t)tw * th;
   if (t >= per * nViews) return;
   const int v = (int)(t / per), q = (int)(t % per);
-  const int y = q / twD, x = q % twD;
-  const float* src = tiles + (size_t)v * perView + offSrc;
-  const int x0 = 2 * x, x1 = min(2 * x + 1, twS - 1), y0 = 2 * y, y1 = min(2 * y + 1, thS - 1);
-  const float m = fmaxf(fmaxf(src[y0 * twS + x0], src[y0 * twS + x1]), fmaxf(src[y1 * twS + x0], src[y1 * twS + x1]));
-  tiles[(size_t)v * perView + offDst + q] = m;
+  const int y = q / tw, x = q % tw, h = 1 << (l - 1);
+  const int x1 = min(x + h, tw - 1), y1 = min(y + h, th - 1);
+  const float* src = tiles + (size_t)v * perView + (size_t)(l - 1) * per;
+  float* dst = tiles + (size_t)v * perView + (size_t)l * per;
+  dst[q] = fmaxf(fmaxf(src[y * tw + x], src[y * tw + x1]), fmaxf(src[y1 * tw + x], src[y1 * tw + x1]));
+  const float* srn = src + minOff;
+  dst[minOff + q] = fminf(fminf(srn[y * tw + x], srn[y * tw + x1]), fminf(srn[y1 * tw + x], srn[y1 * tw + x1]));
+}
+
+// flag = 1.0f when some tile of the view is fully valid (its min statistic is finite or +inf)
+__global__ void __launch_bounds__(256) view_flag_kernel(float* __restrict__ tiles, int perView, int minOff, int flagOff, int n0)
+{
+  const float* t = tiles + (size_t)blockIdx.x * perView + minOff;
+  int any = 0;
+  for (int q = threadIdx.x; q < n0; q += blockDim.x) any |= (t[q] > -INFINITY) ? 1 : 0;
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) tiles[(size_t)blockIdx.x * perView + flagOff] = any ? 1.0f : 0.0f;
 }
 
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 float* d_cls, long long clsSpare, float* d_tileDmax, cudaStream_t s)
+                                 float* d_cls, long long clsSpare, float* d_tileStats, cudaStream_t s)
 {
   const TilePyramid p = tile_pyramid_layout(W, H);
-  const size_t tiles = (size_t)p.tw[0] * p.th[0] * nViews;
-  if (tiles == 0) return cudaSuccess;
-  const unsigned blocks = (unsigned)((tiles + 7) / 8);
-  prepare_views_kernel<<<blocks, 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw[0], p.th[0], p.perView, d_cls, clsSpare, d_tileDmax);
+  const size_t blocks2x2 = (size_t)((p.tw + 1) / 2) * ((p.th + 1) / 2) * nViews;
+  if (blocks2x2 == 0) return cudaSuccess;
+  prepare_views_kernel<<<(unsigned)((blocks2x2 + 7) / 8), 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw, p.th, p.perView,
+                                                                       p.minOff, d_cls, clsSpare, d_tileStats);
+  const size_t n = (size_t)p.tw * p.th * nViews;
   for (int l = 1; l < p.nLevels; l++)
-  {
-    const size_t n = (size_t)p.tw[l] * p.th[l] * nViews;
-    tile_pyramid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_tileDmax, nViews, p.perView, p.off[l - 1], p.tw[l - 1],
-                                                                  p.th[l - 1], p.off[l], p.tw[l], p.th[l]);
-  }
+    tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_tileStats, nViews, p.perView, p.minOff, p.tw, p.th, l);
+  view_flag_kernel<<<nViews, 256, 0, s>>>(d_tileStats, p.perView, p.minOff, p.flagOff, p.tw * p.th);
   return cudaGetLastError();
 }
 

@@ -123,11 +123,13 @@ def make_cameras(n_views: int, width: int, height: int, seed: int = DEFAULT_SEED
 
 def render_views(K: np.ndarray, RT: np.ndarray, width: int, height: int, *, seed: int = DEFAULT_SEED,
                  first_view: int = 0, device="cpu", depth_noise: float = 0.0, want_color: bool = True,
-                 want_best_cost: bool = True):
+                 want_best_cost: bool = True, cost_model: str = "iid"):
     """Ray-cast the unit sphere for views K/RT (their global indices start at ``first_view``).
 
     Returns (depths f64 [n,H,W], best_cost f64 [n,H,W] or None, colors u8 [n,H,W,3] or None),
-    all with bottom-up rows.
+    all with bottom-up rows.  ``cost_model``: "iid" = every pixel's best cost is an independent uniform in
+    [0, 0.2) (salt-and-pepper holes after the 0.14 filter, ~30 % of the pixels); "coherent" = smooth value
+    noise on a 48-pixel lattice in [0, 0.2) (the filter removes connected regions instead).
     """
     n = K.shape[0]
     dev = torch.device(device)
@@ -161,7 +163,25 @@ def render_views(K: np.ndarray, RT: np.ndarray, width: int, height: int, *, seed
              + _uniform(pix, seed + 14) - 2.0) * math.sqrt(3.0)      # ~N(0,1)
         depth = depth + depth_noise * g
     depths = torch.where(hit, depth, torch.full_like(depth, -1.0)).contiguous()
-    best = (_uniform(pix, seed + 1) * 0.2).contiguous() if want_best_cost else None
+    best = None
+    if want_best_cost and cost_model == "iid":
+        best = (_uniform(pix, seed + 1) * 0.2).contiguous()
+    elif want_best_cost and cost_model == "coherent":
+        L = 48
+        nx, ny = W // L + 2, H // L + 2
+        gx = torch.arange(W, device=dev, dtype=torch.float64).view(1, 1, W) / L
+        gy = torch.arange(H, device=dev, dtype=torch.float64).view(1, H, 1) / L
+        ix, iy = gx.floor().to(torch.int64), gy.floor().to(torch.int64)
+        wx, wy = gx - ix, gy - iy
+        wx, wy = wx * wx * (3.0 - 2.0 * wx), wy * wy * (3.0 - 2.0 * wy)
+
+        def node(ax, ay):
+            return _uniform(vidx * (nx * ny) + ay * nx + ax, seed + 1)
+        best = ((node(ix, iy) * (1 - wx) + node(ix + 1, iy) * wx) * (1 - wy)
+                + (node(ix, iy + 1) * (1 - wx) + node(ix + 1, iy + 1) * wx) * wy) * 0.2
+        best = best.expand(n, H, W).contiguous()
+    elif want_best_cost:
+        raise ValueError("cost_model must be 'iid' or 'coherent'")
     colors = None
     if want_color:
         chans = []

@@ -152,10 +152,11 @@ int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
 
 /* Diagnostics of the certified fast path (DMI_OPT_TIER_COUNTERS = 1): out[0] voxel*views certified by
  * the FP32 tier, [1] sent to the FP64 tier, [2] sent to the exact tier, [3] exact because |diff| was
- * within the guard band of Delta, [4] voxel*views processed after culling, [5] (brick, view) pairs
- * culled, [6] voxel*views in the FP64 band around the surface, [7] (brick, view) pairs seen.
- * Reading resets the counters. */
-int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[8]);
+ * within the guard band of Delta, [4] voxel*views evaluated one by one after culling, [5] (brick, view)
+ * pairs culled, [6] voxel*views in the FP64 band around the surface, [7] (brick, view) pairs seen,
+ * [8] (brick, view) pairs settled brick-wide as free space in front of the surface (one add per voxel),
+ * [9..15] reserved (0).  Reading resets the counters. */
+int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[16]);
 
 /* ---- mesh coloration ----------------------------------------------------------------------- */
 

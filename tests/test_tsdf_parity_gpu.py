@@ -105,6 +105,46 @@ def test_accumulates_onto_io_scalar_and_view_order(gpu_ctx, oracle, kernel):
 
 
 @pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
+def test_zero_and_negative_zero_io_scalar(gpu_ctx, oracle, kernel):
+    """An all-zero io_scalar is not uploaded (the library scans it on the host); -0.0 is NOT zero bits:
+    voxels no view touches must keep their sign, as in the reference."""
+    s = Scene(40, 6, 96, 72)
+    for fill in (0.0, -0.0):
+        start = np.full(s.grid.n_voxels, fill)
+        start[17] = 0.0 if fill == 0.0 else 0.25          # one odd element in the -0.0 case
+        want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, None, 0.0, s.K, s.RT, start.copy())
+        got = run_gpu(gpu_ctx, s, np.float64, best_cost=False, start=start, kernel=kernel)
+        if kernel == _lib.DMI_TSDF_KERNEL_EXACT:
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+        else:
+            # the fast path proves "contributes 0" without performing the reference's `+= 0.0`, which would
+            # turn a -0.0 into +0.0: values are equal, the sign of a zero may differ (DESIGN.md, certification)
+            assert_close(got, want)
+            nz = want != 0
+            assert np.array_equal(np.signbit(got[nz]), np.signbit(want[nz]))
+
+
+def test_large_io_scalar_with_one_hidden_nonzero_voxel(gpu_ctx, oracle):
+    """>= 256 MB io_scalar: dmi_process_depth_maps integrates onto a zeroed device volume while a host scan
+    verifies that io_scalar really is all zero; one non-zero voxel the quick probe does not see must send
+    the call through the upload path (the pass is repeated) and give the reference's result."""
+    s = Scene(324, 2, 96, 72)
+    start = s.zeros()
+    assert start.nbytes >= (256 << 20)
+    start[12345677] = 0.5
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, start.copy())
+    got = run_gpu(gpu_ctx, s, np.float64, start=start)
+    assert got[12345677] == want[12345677] and want[12345677] != 0
+    assert np.array_equal(got != 0, want != 0)
+    assert_close(got, want)
+    # and the all-zero case of the same size (speculation confirmed)
+    want0 = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    got0 = run_gpu(gpu_ctx, s, np.float64)
+    assert np.array_equal(got0 != 0, want0 != 0)
+    assert_close(got0, want0)
+
+
+@pytest.mark.parametrize("kernel", [_lib.DMI_TSDF_KERNEL_EXACT, _lib.DMI_TSDF_KERNEL_AUTO])
 def test_z_slabs_concatenate_bit_identically(gpu_ctx, kernel):
     s = Scene((37, 21, 19), 5, 80, 60, rotate_deg=30.0)
     whole = run_gpu(gpu_ctx, s, np.float64, kernel=kernel)
@@ -147,6 +187,34 @@ def test_brick_culling_is_conservative(gpu_ctx, oracle):
             assert counters["culled_brick_views"] >= 0
     assert np.array_equal(outs[0], outs[1])
     want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    assert np.array_equal(outs[0] != 0, want != 0)
+    assert_close(outs[0], want)
+
+
+@pytest.mark.parametrize("best_cost", [True, False])
+def test_free_space_bricks_are_settled_exactly(gpu_ctx, oracle, best_cost):
+    """(brick, view) pairs whose voxels all lie farther than Delta in front of fully valid depth tiles get
+    -Eta*Rho by one add per voxel, without projecting them: must not change a bit against the kernel with
+    the brick tests disabled, and must happen (coherent best-cost maps / no filter leave fully valid tiles)."""
+    # 1.5 pixels per voxel: a brick's footprint is a few 8-pixel tiles
+    s = Scene(128, 12, 320, 240, rotate_deg=30.0, depth_noise=0.25, cost_model="coherent")
+    ctx = gpu_ctx
+    outs = []
+    for cull in (1, 0):
+        ctx.set_option(_lib.DMI_OPT_CULL, cull)
+        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 1)
+        try:
+            outs.append(run_gpu(ctx, s, np.float64, best_cost=best_cost))
+            counters = ctx.tsdf_tier_counters()
+        finally:
+            ctx.set_option(_lib.DMI_OPT_CULL, 1)
+            ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 0)
+        if cull:
+            assert counters["uniform_front"] > 0
+        else:
+            assert counters["uniform_front"] == 0
+    assert np.array_equal(outs[0], outs[1])
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost if best_cost else None, 0.14, s.K, s.RT, s.zeros())
     assert np.array_equal(outs[0] != 0, want != 0)
     assert_close(outs[0], want)
 
