@@ -574,6 +574,8 @@ def main():
             u = max(tiers["units"], 1)
             roofline["tiers"] = {"fp32_certified": tiers["t1_certified"] / u, "fp64_tier": tiers["t2_entered"] / u,
                                  "exact_tier": tiers["t3_entered"] / u, "band_fp64": tiers["near_band"] / u,
+                                 "far_front": tiers["far_front"] / u, "far_behind": tiers["far_behind"] / u,
+                                 "invalid_or_rejected": tiers["invalid_or_rejected"] / u,
                                  "note": "fractions of the evaluated pairs (rank 0)"}
         line = {
             "metric": "voxel*view updates/sec", "value": value, "unit": "voxel*views/s", "n_gpus": world,

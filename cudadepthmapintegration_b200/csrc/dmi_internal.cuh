@@ -72,7 +72,7 @@ struct FastCounters               // optional diagnostics (device memory, may be
 {
   unsigned long long t1_certified, t2_entered, t3_entered, delta_guard, units, culled, near_band, brick_views;
   unsigned long long uniform_front;     // (brick, view) pairs settled by one add per voxel, see eval_box
-  unsigned long long reserved[7];
+  unsigned long long reserved[7];       // [0] far in front, [1] far behind, [2] invalid pixel (voxel*views, FP32 phase C)
 };
 
 // Per-view data the fast kernel gathers from, built by launch_prepare_views:

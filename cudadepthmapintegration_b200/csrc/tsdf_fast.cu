@@ -407,7 +407,7 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   const int negW = -W;
   const double delta = g.delta, thick = g.thick;
   const T nerT = (T)g.neg_eta_rho;
-  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0, n_uf = 0;
+  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0, n_uf = 0, n_front = 0, n_behind = 0, n_inv = 0;
 
   for (int q = 0; q < nsurv; q++)
   {
@@ -536,6 +536,12 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
           const int m = h * HM + mm;
           const float fc = PINHOLE ? fmaf((float)m, kz, fhz0) : fmaf((float)m, kc, fcz0);   // camera z (:207)
           classify_far(acc[m], near, nerT, fc, d32[m], thrfar, 1u << m);
+          if (COUNT)
+          {
+            const float df = fc - d32[m];
+            if (d32[m] == -1.0f) n_inv++;
+            else if (fabsf(df) > thrfar) { if (df < 0.f) n_front++; else n_behind++; }
+          }
         }
       }
     }
@@ -586,9 +592,9 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   {
     // one atomic per warp and counter (the lanes that returned early above are simply absent)
     const unsigned act = __activemask();
-    unsigned long long vals[6] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)FM * (nsurv - n_uf)};
+    unsigned long long vals[9] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)FM * (nsurv - n_uf), n_front, n_behind, n_inv};
 #pragma unroll
-    for (int q = 0; q < 6; q++)
+    for (int q = 0; q < 9; q++)
     {
       unsigned long long x = vals[q];
       for (int o = 16; o > 0; o >>= 1)
@@ -606,6 +612,9 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
       atomicAdd(&counters->delta_guard, vals[3]);
       atomicAdd(&counters->near_band, vals[4]);
       atomicAdd(&counters->units, vals[5]);
+      atomicAdd(&counters->reserved[0], vals[6]);
+      atomicAdd(&counters->reserved[1], vals[7]);
+      atomicAdd(&counters->reserved[2], vals[8]);
     }
   }
 }

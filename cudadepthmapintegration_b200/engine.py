@@ -191,7 +191,8 @@ class Context:
         out = (C.c_ulonglong * 16)()
         self._ck(self._lib.dmi_tsdf_tier_counters(self._h, out))
         return dict(zip(("t1_certified", "t2_entered", "t3_entered", "delta_guard", "units", "culled_brick_views",
-                         "near_band", "brick_views", "uniform_front"), [int(x) for x in out]))
+                         "near_band", "brick_views", "uniform_front", "far_front", "far_behind", "invalid_or_rejected"),
+                        [int(x) for x in out]))
 
     # -- coloration ------------------------------------------------------------------------------
     def colorize(self, xyz: np.ndarray, colors: np.ndarray, K, RT, width: int, height: int):

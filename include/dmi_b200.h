@@ -155,7 +155,8 @@ int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
  * within the guard band of Delta, [4] voxel*views evaluated one by one after culling, [5] (brick, view)
  * pairs culled, [6] voxel*views in the FP64 band around the surface, [7] (brick, view) pairs seen,
  * [8] (brick, view) pairs settled brick-wide as free space in front of the surface (one add per voxel),
- * [9..15] reserved (0).  Reading resets the counters. */
+ * [9] voxel*views classified far in front of the depth, [10] far behind it, [11] on an invalid pixel
+ * (or rejected: behind the camera / outside the image) by the FP32 phase, [12..15] reserved (0).  Reading resets the counters. */
 int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[16]);
 
 /* ---- mesh coloration ----------------------------------------------------------------------- */
