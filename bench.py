@@ -329,13 +329,15 @@ def main():
     if world > 1 and args.exchange == "ce":
         # the resident view buffers are allocated by the library (plain cudaMalloc) so that every rank can map
         # every other rank's buffers through CUDA IPC and PUSH its share with the copy engines over NVLink.
-        # One allocation: [depth f64 V*npix][classification f32, per group: n*npix + 4 spare][tile pyramids f32]
+        # One allocation: [residual i32 V*npix][classification f32, per group: n*npix + 4 spare][tile statistics f32];
+        # (classification, residual) is the lossless 8-byte split form of the filtered double depth, so the
+        # exchange moves 8 bytes per pixel and no rank prepares a view it does not own.
         ncls, ntile = ctx.prepared_view_sizes()
         cls_off, acc = {}, 0
         for (g0, g1) in groups:
             cls_off[g0] = acc
             acc += (g1 - g0) * ncls + 4
-        depth_bytes = V * npix * 8
+        depth_bytes = V * npix * 4
         cls_bytes = (acc * 4 + 255) // 256 * 256
         own_ptr = ctx.device_malloc(depth_bytes + cls_bytes + V * ntile * 4)
         cls_ptr, tile_ptr = own_ptr + depth_bytes, own_ptr + depth_bytes + cls_bytes
@@ -343,8 +345,8 @@ def main():
         class _Buf:
             pass
         hb = _Buf()
-        hb.__cuda_array_interface__ = {"shape": (V, H, W), "typestr": "<f8", "data": (own_ptr, False), "version": 3}
-        all_depths = torch.as_tensor(hb, device=dev)
+        hb.__cuda_array_interface__ = {"shape": (V, H, W), "typestr": "<i4", "data": (own_ptr, False), "version": 3}
+        all_depths = torch.as_tensor(hb, device=dev)          # the residual images, viewed as a tensor
         handles = [None] * world
         dist.all_gather_object(handles, ctx.ipc_get_handle(own_ptr))
         peer_ptr = [own_ptr if r == rank else ctx.ipc_open_handle(handles[r]) for r in range(world)]
@@ -387,14 +389,31 @@ def main():
         h.__cuda_array_interface__ = {"shape": (slab_cells,), "typestr": "<f8", "data": (ptr, False), "version": 3}
         return torch.as_tensor(h, device=dev)
 
-    def step_device():
-        """One full job with inputs resident in HBM."""
+    h2d_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    def step_device(host=None):
+        """One full job with inputs resident in HBM (host = (depths, cost) pinned tensors: end-to-end variant,
+        each group's share is uploaded on its own stream while the previous groups are integrated)."""
         ctx.volume_begin(None, np.float64)
         if world == 1:
             ctx.volume_integrate_device(V, my_depths.data_ptr(), my_cost.data_ptr(), THRESH, K, RT)
             return
         cur = torch.cuda.current_stream()
         comm_stream.wait_stream(cur)
+        uploaded = []
+        if host is not None:
+            h2d_stream.wait_stream(cur)          # the previous step is done with my_depths / my_cost
+            o = 0
+            with torch.cuda.stream(h2d_stream):
+                for (g0, g1) in groups:
+                    a, b, _ = owned(g0, g1)
+                    if b > a:
+                        my_depths[o:o + b - a].copy_(host[0][o:o + b - a], non_blocking=True)
+                        my_cost[o:o + b - a].copy_(host[1][o:o + b - a], non_blocking=True)
+                        o += b - a
+                    ev = torch.cuda.Event()
+                    ev.record(h2d_stream)
+                    uploaded.append(ev)
         if args.breakdown:
             for nm in ("t0", "comm_done", "compute_done", "gather_done"):
                 marks[nm] = torch.cuda.Event(enable_timing=True)
@@ -405,9 +424,11 @@ def main():
         with torch.cuda.stream(comm_stream):
             if peer_ptr is not None:
                 dist.all_reduce(fence)          # every rank is done reading the previous step's views
-            for (g0, g1) in groups:
+            for gi, (g0, g1) in enumerate(groups):
                 a, b, per = owned(g0, g1)
                 n = b - a
+                if uploaded:
+                    comm_stream.wait_event(uploaded[gi])
                 if peer_ptr is None:
                     if n > 0:
                         all_depths[a:b].copy_(my_depths[off:off + n])
@@ -423,12 +444,11 @@ def main():
                         ctx.set_stream(comm_stream.cuda_stream)
                         c_rel = (cls_off[g0] + (a - g0) * ncls) * 4
                         ctx.prepare_views_device(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
-                                                 cls_ptr + c_rel, -1, tile_ptr + a * ntile * 4)
-                        ctx.memcpy_device_async(own_ptr + a * npix * 8, my_depths[off:off + n].data_ptr(), n * npix * 8)
+                                                 cls_ptr + c_rel, -1, tile_ptr + a * ntile * 4, d_lo=own_ptr + a * npix * 4)
                         for r in range(1, world):      # staggered order: every link busy, no hot receiver
                             dst = (rank + r) % world
                             base = peer_ptr[dst]
-                            ctx.memcpy_device_async(base + a * npix * 8, my_depths[off:off + n].data_ptr(), n * npix * 8)
+                            ctx.memcpy_device_async(base + a * npix * 4, own_ptr + a * npix * 4, n * npix * 4)
                             ctx.memcpy_device_async(base + depth_bytes + c_rel, cls_ptr + c_rel, n * ncls * 4)
                             ctx.memcpy_device_async(base + depth_bytes + cls_bytes + a * ntile * 4, tile_ptr + a * ntile * 4, n * ntile * 4)
                         ctx.set_stream(cur.cuda_stream)
@@ -448,8 +468,8 @@ def main():
             if peer_ptr is None:
                 ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
             else:
-                ctx.volume_integrate_prepared(g1 - g0, own_ptr + g0 * npix * 8, cls_ptr + cls_off[g0] * 4, (g1 - g0) * ncls,
-                                              tile_ptr + g0 * ntile * 4, K[g0:g1], RT[g0:g1])
+                ctx.volume_integrate_prepared(g1 - g0, None, cls_ptr + cls_off[g0] * 4, (g1 - g0) * ncls,
+                                              tile_ptr + g0 * ntile * 4, K[g0:g1], RT[g0:g1], d_lo=own_ptr + g0 * npix * 4)
             if args.breakdown:
                 gb.record(cur)
                 marks["groups"].append((ga, gb))
@@ -633,9 +653,7 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
         h2d = int(2 * nmine * npix * 8)
     else:
         def step():
-            my_depths.copy_(h_depths, non_blocking=True)
-            my_cost.copy_(h_cost, non_blocking=True)
-            step_device()
+            step_device(host=(h_depths, h_cost))
             h_vol.copy_(slab_tensor(), non_blocking=True)
         api = "per rank: H2D of its share of the views, owner-side preparation + exchange, integration of its z-slab, D2H of its slab"
         h2d = int(2 * nmine * npix * 8)

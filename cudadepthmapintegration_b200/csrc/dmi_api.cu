@@ -388,7 +388,7 @@ static int integrate_exact_resident(dmi_ctx* ctx, int nViews, const double* d_de
 
 // Fast kernel over views that are ALREADY prepared (classification images + tile pyramids, see
 // launch_prepare_views): composes the per-view rows and launches chunk by chunk.
-static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const float* d_cls, long long clsSpare,
+static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo, const float* d_cls, long long clsSpare,
                                    const float* d_tiles, const double* K, const double* RT)
 {
   const dmi::GridParams& g = ctx->g;
@@ -413,7 +413,7 @@ static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_dep
       memcpy(c->e[q].K, k16, sizeof(double) * 12);
       if (!(k16[8] == 0.0 && k16[9] == 0.0 && k16[10] == 1.0 && k16[11] == 0.0)) c->pinhole = 0;
     }
-    DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths + npix * v0, d_cls + npix * v0, clsSpare - (long long)(npix * (size_t)v0),
+    DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths ? d_depths + npix * v0 : nullptr, d_lo ? d_lo + npix * v0 : nullptr, d_cls + npix * v0, clsSpare - (long long)(npix * (size_t)v0),
                                  d_tiles + tilesPerView * v0, ctx->opt_cull, (dmi::ViewFast*)ctx->viewscratch.p,
                                  (unsigned*)ctx->maskscratch.p, ctx->vol.p, ctx->vol_type,
                                  ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr, ctx->stream));
@@ -442,9 +442,9 @@ static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_dep
   {
     const int gn = std::min(group, nViews - g0);
     DMI_CK(dmi::launch_prepare_views(d_depths + npix * g0, d_cost ? d_cost + npix * g0 : nullptr, thr, gn, g.W, g.H,
-                                     (float*)ctx->cls.p, (long long)(npix * (size_t)gn), (float*)ctx->tiles.p, ctx->stream));
+                                     (float*)ctx->cls.p, nullptr, (long long)(npix * (size_t)gn), (float*)ctx->tiles.p, ctx->stream));
     ctx->total_launches++;
-    int rc = integrate_fast_prepared(ctx, gn, d_depths + npix * g0, (const float*)ctx->cls.p, (long long)(npix * (size_t)gn),
+    int rc = integrate_fast_prepared(ctx, gn, d_depths + npix * g0, nullptr, (const float*)ctx->cls.p, (long long)(npix * (size_t)gn),
                                      (const float*)ctx->tiles.p, K + 16 * (size_t)g0, RT + 16 * (size_t)g0);
     if (rc != DMI_OK) return rc;
   }
@@ -513,33 +513,33 @@ int dmi_prepared_view_sizes(dmi_ctx* ctx, size_t* clsFloatsPerView, size_t* tile
 }
 
 int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
-                             double thresholdBestCost, float* d_cls, long long clsSpareIndex, float* d_tileStats)
+                             double thresholdBestCost, float* d_cls, int* d_lo, long long clsSpareIndex, float* d_tileStats)
 {
   if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
   if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
   if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
   DMI_REQUIRE(d_depths && d_cls && d_tileStats, "null argument");
   DMI_CK(cudaSetDevice(ctx->device));
-  DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, d_cls, clsSpareIndex,
+  DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, d_cls, d_lo, clsSpareIndex,
                                    d_tileStats, ctx->stream));
   ctx->total_launches++;
   return DMI_OK;
 }
 
-int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const float* d_cls,
+int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo, const float* d_cls,
                                   long long clsSpareIndex, const float* d_tileStats, const double* K, const double* RT)
 {
   if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
   if (!ctx->initialized || !ctx->vol_active) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_volume_begin has not been called");
   if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
-  DMI_REQUIRE(d_depths && d_cls && d_tileStats && K && RT, "null argument");
+  DMI_REQUIRE((d_depths || d_lo) && d_cls && d_tileStats && K && RT, "null argument");
   if (!fast_path_applies(ctx))
     return ctx->fail(DMI_ERR_BAD_PARAMETERS, "prepared views need the certified fast path (0 < Thick, finite parameters, kernel AUTO)");
   DMI_CK(cudaSetDevice(ctx->device));
   if (slab_cells(ctx->g) == 0) return DMI_OK;
   EventSpan span = ctx->tsdf_stats.open();
   DMI_CK(cudaEventRecord(span.a, ctx->stream));
-  int rc = integrate_fast_prepared(ctx, nViews, d_depths, d_cls, clsSpareIndex, d_tileStats, K, RT);
+  int rc = integrate_fast_prepared(ctx, nViews, d_depths, d_depths ? nullptr : d_lo, d_cls, clsSpareIndex, d_tileStats, K, RT);
   if (rc != DMI_OK) return rc;
   DMI_CK(cudaEventRecord(span.b, ctx->stream));
   ctx->tsdf_stats.pending.push_back(span);

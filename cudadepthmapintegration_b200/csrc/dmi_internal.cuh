@@ -96,10 +96,12 @@ struct TilePyramid
 };
 TilePyramid tile_pyramid_layout(int W, int H);
 // clsSpare: index (relative to d_cls) of a float that is set to -1.0f for the rejected voxels' gathers; < 0 = none
+// d_lo (may be null): residual image of the lossless split depth = (cls, lo), see split_encode
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 float* d_cls, long long clsSpare, float* d_tileDmax, cudaStream_t s);
+                                 float* d_cls, int* d_lo, long long clsSpare, float* d_tileDmax, cudaStream_t s);
 // d_cls[clsSpare] (an index relative to d_cls) must hold -1.0f: launch_prepare_views(n views) writes it at n*W*H
-cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
+// d_depths null: the double depths are rebuilt from (d_cls, d_lo)
+cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
                              ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
                              FastCounters* d_counters, cudaStream_t s);

@@ -35,11 +35,33 @@ __device__ __forceinline__ T ray_potential(const GridParams& g, double realDista
 // `cls` (optional): the float classification image of the fast path, in which -1.0f marks exactly the
 // pixels that are invalid AFTER the best-cost filter (ReconstructionData.cxx:159-166); `depth` may then
 // be the caller's unfiltered map, whose valid pixels the filter leaves untouched.
+// Lossless split of a depth d into hi = the float of the classification image and lo = (d - hi) in units of
+// 2^(e - 53), e = max(exponent(hi), -64): d - hi is exact (hi is d rounded to float, or a neighbour), at most
+// 1.5 float ulps = 1.5 * 2^30 units, and a multiple of the unit whenever |d| >= 2^-64 (or d == 0).  8 bytes
+// per pixel carry the classification image AND the exact double depth.  Non-finite hi: lo = 0, d = hi.
+__device__ __forceinline__ int split_exponent(float hi)
+{
+  return max(((__float_as_int(hi) >> 23) & 0xff) - 127, -64);
+}
+__device__ __forceinline__ int split_encode(double d, float hi)
+{
+  if (!(fabsf(hi) <= 3.402823466e+38f)) return 0;
+  const double scale = __hiloint2double((1023 + 53 - split_exponent(hi)) << 20, 0);   // 2^(53 - e)
+  return __double2int_rn(__dmul_rn(__dsub_rn(d, (double)hi), scale));
+}
+__device__ __forceinline__ double split_decode(float hi, int lo)
+{
+  const double unit = __hiloint2double((1023 - 53 + split_exponent(hi)) << 20, 0);    // 2^(e - 53)
+  return __fma_rn((double)lo, unit, (double)hi);
+}
+
+// `depth` may be null when `lo` (the split residual image, with `cls` as its hi part) is given.
 template <typename T>
 __device__ __forceinline__ void integrate_exact(const GridParams& g, const ViewExact& V,
                                                 const double* __restrict__ depth,
                                                 double wx, double wy, double wz, T& acc,
-                                                const float* __restrict__ cls = nullptr)
+                                                const float* __restrict__ cls = nullptr,
+                                                const int* __restrict__ lo = nullptr)
 {
   const double cx = row_point(V.RT + 0, wx, wy, wz);
   const double cy = row_point(V.RT + 4, wx, wy, wz);
@@ -55,7 +77,7 @@ __device__ __forceinline__ void integrate_exact(const GridParams& g, const ViewE
   if (px < 0 || py < 0 || px >= g.W || py >= g.H) return;   // :192-197
   const size_t id = (size_t)g.W * (size_t)(g.H - 1 - py) + px;                 // :141-149
   if (cls && __ldg(cls + id) == -1.0f) return;          // filtered out, or -1 in the file
-  const double d = __ldg(depth + id);                   // :201
+  const double d = lo ? split_decode(__ldg(cls + id), __ldg(lo + id)) : __ldg(depth + id);   // :201
   if (d == -1) return;                                  // :202
   acc += ray_potential<T>(g, cz, d);                    // :207-211
 }

@@ -105,11 +105,11 @@ __device__ __forceinline__ double affine(const double* r, double di, double dj, 
 // caller's accumulators stay in registers.
 template <typename T>
 __device__ __noinline__ T exact_unit(const GridParams* g, const ViewExact* e, const double* depth,
-                                     const float* cls, int i, int j, int k, T acc)
+                                     const float* cls, const int* lo, int i, int j, int k, T acc)
 {
   double wx, wy, wz;
   voxel_world(*g, i, j, k, wx, wy, wz);
-  integrate_exact<T>(*g, *e, depth, wx, wy, wz, acc, cls);
+  integrate_exact<T>(*g, *e, depth, wx, wy, wz, acc, cls, lo);
   return acc;
 }
 
@@ -302,10 +302,12 @@ __device__ __forceinline__ int nth_set_bit64(unsigned lo, unsigned hi, int n)
   return n < nlo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - nlo + 1);
 }
 
-template <typename T, bool PINHOLE, bool COUNT>
+// SPLIT: the double depths are not resident; the band and the exact tier rebuild them from the classification
+// image and the residual image `lo` (split_decode), bit for bit.
+template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
 __global__ void __launch_bounds__(FT)
 tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
-                 const double* __restrict__ depths, const float* __restrict__ cls,
+                 const double* __restrict__ depths, const int* __restrict__ lo, const float* __restrict__ cls,
                  const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
                  long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
                  T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters)
@@ -432,8 +434,9 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
     // storage row (H-1-py) of the bottom-up image (CudaReconstruction.cu:141-149): index = px - py*W from here
     const size_t voff = npix * v + (size_t)(H - 1) * W;
     const float* cv = cls + voff;
-    const double* dv = depths + voff;
-    asm volatile("" : "+l"(cv), "+l"(dv));                    // keep them as plain 64-bit registers
+    const double* dv = SPLIT ? nullptr : depths + voff;
+    const int* lv = SPLIT ? lo + voff : nullptr;
+    asm volatile("" : "+l"(cv), "+l"(dv), "+l"(lv));          // keep them as plain 64-bit registers
     // rejected voxels gather the spare float behind the classification images, which holds -1.0f:
     // no predicate, no default value, one sector for the whole warp
     const int rej = (int)(clsSpare - (long long)voff);
@@ -516,7 +519,8 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
         if (need3 & (1u << m))
         {
           if (COUNT) n_t3++;
-          acc[m] = exact_unit<T>(&g, &c.e[v], depths + npix * v, cls + npix * v, i, j, k0 + m, acc[m]);
+          acc[m] = exact_unit<T>(&g, &c.e[v], SPLIT ? nullptr : depths + npix * v, cls + npix * v,
+                                 SPLIT ? lo + npix * v : nullptr, i, j, k0 + m, acc[m]);
         }
     }
     if (!anyh[0] && !anyh[1]) continue;
@@ -552,7 +556,11 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
       const double czk = S.czr[2], gd = S.gd;
       double dd[FM];
 #pragma unroll
-      for (int m = 0; m < FM; m++) dd[m] = (near & (1u << m)) ? __ldg(dv + idx[m]) : 0.0;
+      for (int m = 0; m < FM; m++)
+      {
+        if (SPLIT) dd[m] = (near & (1u << m)) ? split_decode(d32[m], __ldg(lv + idx[m])) : 0.0;
+        else dd[m] = (near & (1u << m)) ? __ldg(dv + idx[m]) : 0.0;
+      }
 #pragma unroll
       for (int m = 0; m < FM; m++)
       {
@@ -568,7 +576,8 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
           if (fabs(td) < gd)
           {
             if (COUNT) n_dg++;
-            acc[m] = exact_unit<T>(&g, &c.e[v], depths + npix * v, cls + npix * v, i, j, k0 + m, acc[m]);
+            acc[m] = exact_unit<T>(&g, &c.e[v], SPLIT ? nullptr : depths + npix * v, cls + npix * v,
+                                   SPLIT ? lo + npix * v : nullptr, i, j, k0 + m, acc[m]);
           }
           else if (td > 0.0)
           {
@@ -633,7 +642,7 @@ __global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant_
 }
 
 template <typename T, bool PINHOLE>
-static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths,
+static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                            const float* d_cls, const float* d_tileDmax, const TilePyramid& pyr, bool cull,
                            long long clsSpare, const ViewFast* d_views, unsigned* d_masks, T* d_vol, int nbi, int nbj,
                            int nbk, FastCounters* d_counters, cudaStream_t s)
@@ -644,10 +653,12 @@ static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& 
     supertile_cull_kernel<PINHOLE><<<(nst + 3) / 4, 256, 0, s>>>(g, c, d_tileDmax, pyr, d_views, nbi, nbj, nbk, d_masks, nst);
   }
   const unsigned* masks = (cull && d_masks) ? d_masks : nullptr;
-  if (d_counters)
-    tsdf_fast_kernel<T, PINHOLE, true><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, d_vol, nbi, nbj, nbk, d_counters);
-  else
-    tsdf_fast_kernel<T, PINHOLE, false><<<grid, FT, 0, s>>>(g, c, d_depths, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, d_vol, nbi, nbj, nbk, nullptr);
+#define DMI_LAUNCH_FAST(COUNT, SPLIT, CNT)                                                                         \
+  tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT><<<grid, FT, 0, s>>>(g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull ? 1 : 0, \
+                                                                 clsSpare, d_views, masks, d_vol, nbi, nbj, nbk, CNT)
+  if (d_counters) { if (d_depths) DMI_LAUNCH_FAST(true, false, d_counters); else DMI_LAUNCH_FAST(true, true, d_counters); }
+  else { if (d_depths) DMI_LAUNCH_FAST(false, false, nullptr); else DMI_LAUNCH_FAST(false, true, nullptr); }
+#undef DMI_LAUNCH_FAST
 }
 
 size_t tsdf_fast_mask_bytes(const GridParams& g)
@@ -657,7 +668,7 @@ size_t tsdf_fast_mask_bytes(const GridParams& g)
   return std::max<size_t>(8, nsi * nsj * nsk * 8);
 }
 
-cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths,
+cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
                              ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
                              FastCounters* d_counters, cudaStream_t s)
@@ -672,13 +683,13 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
   const ViewFast* d_views = d_viewScratch;
   if (scalarType == 1)
   {
-    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
-    else launch_variant<double, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
+    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
+    else launch_variant<double, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
   }
   else
   {
-    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
-    else launch_variant<float, false>(grid, g, c, d_depths, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
+    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
+    else launch_variant<float, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
   }
   return cudaGetLastError();
 }
@@ -704,7 +715,7 @@ TilePyramid tile_pyramid_layout(int W, int H)
 __global__ void __launch_bounds__(256)
 prepare_views_kernel(const double* __restrict__ depths, const double* __restrict__ cost, double thr,
                      int nViews, int W, int H, int TW, int TH, int perView, int minOff, float* __restrict__ cls,
-                     long long clsSpare, float* __restrict__ tileStats)
+                     int* __restrict__ lo, long long clsSpare, float* __restrict__ tileStats)
 {
   if (blockIdx.x == 0 && threadIdx.x == 0 && clsSpare >= 0) cls[clsSpare] = -1.0f;   // the spare slot, see phase B
   const int lane = threadIdx.x & 31;
@@ -743,6 +754,7 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
         }
         else dmin = -INFINITY;
         cls[base + col + q] = f;
+        if (lo) lo[base + col + q] = invalid ? 0 : split_encode(d, f);
       }
     }
   }
@@ -790,13 +802,13 @@ __global__ void __launch_bounds__(256) view_flag_kernel(float* __restrict__ tile
 }
 
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 float* d_cls, long long clsSpare, float* d_tileStats, cudaStream_t s)
+                                 float* d_cls, int* d_lo, long long clsSpare, float* d_tileStats, cudaStream_t s)
 {
   const TilePyramid p = tile_pyramid_layout(W, H);
   const size_t blocks2x2 = (size_t)((p.tw + 1) / 2) * ((p.th + 1) / 2) * nViews;
   if (blocks2x2 == 0) return cudaSuccess;
   prepare_views_kernel<<<(unsigned)((blocks2x2 + 7) / 8), 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw, p.th, p.perView,
-                                                                       p.minOff, d_cls, clsSpare, d_tileStats);
+                                                                       p.minOff, d_cls, d_lo, clsSpare, d_tileStats);
   const size_t n = (size_t)p.tw * p.th * nViews;
   for (int l = 1; l < p.nLevels; l++)
     tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_tileStats, nViews, p.perView, p.minOff, p.tw, p.th, l);

@@ -155,14 +155,19 @@ class Context:
         return int(a.value), int(b.value)
 
     def prepare_views_device(self, n_views: int, d_depths: int, d_best_cost: int | None, threshold, d_cls: int,
-                             cls_spare_index: int, d_tiles: int):
+                             cls_spare_index: int, d_tiles: int, d_lo: int | None = None):
+        """d_lo: optional int32 residual image; (cls, lo) is then a lossless 8-byte form of the filtered depth."""
         self._ck(self._lib.dmi_prepare_views_device(self._h, int(n_views), _ptr(int(d_depths)),
                                                     _ptr(int(d_best_cost)) if d_best_cost else None, float(threshold),
-                                                    _ptr(int(d_cls)), int(cls_spare_index), _ptr(int(d_tiles))))
+                                                    _ptr(int(d_cls)), _ptr(int(d_lo)) if d_lo else None,
+                                                    int(cls_spare_index), _ptr(int(d_tiles))))
 
-    def volume_integrate_prepared(self, n_views: int, d_depths: int, d_cls: int, cls_spare_index: int, d_tiles: int, K, RT):
+    def volume_integrate_prepared(self, n_views: int, d_depths: int | None, d_cls: int, cls_spare_index: int, d_tiles: int,
+                                  K, RT, d_lo: int | None = None):
+        """Exactly one of d_depths (double maps) / d_lo (residual image of the split depth) is needed."""
         K = _f64(K, 16); RT = _f64(RT, 16)
-        self._ck(self._lib.dmi_volume_integrate_prepared(self._h, int(n_views), _ptr(int(d_depths)), _ptr(int(d_cls)),
+        self._ck(self._lib.dmi_volume_integrate_prepared(self._h, int(n_views), _ptr(int(d_depths)) if d_depths else None,
+                                                         _ptr(int(d_lo)) if d_lo else None, _ptr(int(d_cls)),
                                                          int(cls_spare_index), _ptr(int(d_tiles)), _ptr(K), _ptr(RT)))
 
     def volume_end(self, h_scalar: np.ndarray | None = None):

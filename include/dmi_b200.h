@@ -123,21 +123,29 @@ int dmi_volume_integrate_device(dmi_ctx* ctx, int nViews, const double* d_depths
 int dmi_volume_end(dmi_ctx* ctx, void* h_scalar);
 
 /* View preparation split from integration, for multi-GPU runs: the rank that loaded a view prepares it
- * ONCE (best-cost filter folded into a float classification image, -1.0f = invalid, plus the tile
- * max-pyramid used for culling) and the prepared arrays are exchanged with the depth maps, instead of
- * every rank preparing every view.
- *   dmi_prepared_view_sizes    floats per view of the two arrays (W*H and the pyramid size)
- *   dmi_prepare_views_device   d_cls[nViews][H][W], d_tileStats[nViews][tileFloatsPerView]; when
- *                              clsSpareIndex >= 0, d_cls[clsSpareIndex] is set to -1.0f
- *   dmi_volume_integrate_prepared  like dmi_volume_integrate_device, on prepared views; d_depths are the
- *                              UNFILTERED maps (only pixels valid in d_cls are read); d_cls[clsSpareIndex]
- *                              must hold -1.0f and lie within 2^31 floats of every view of the call.
+ * ONCE and the prepared arrays are exchanged, instead of every rank preparing every view:
+ *   d_cls        float[nViews][H][W]  classification image: the depth rounded to float, -1.0f = invalid
+ *                                     after the best-cost filter (never -1.0f on a valid pixel)
+ *   d_lo         int32[nViews][H][W]  (optional) residual of the LOSSLESS split depth = (cls, lo): with it the
+ *                                     double depth maps need not be exchanged or kept, 8 bytes per pixel
+ *                                     carry everything (exact for |depth| >= 2^-64 or 0; smaller magnitudes
+ *                                     keep 2^-117 absolute accuracy)
+ *   d_tileStats  float[nViews][tileFloatsPerView]  tile statistics used by the brick tests
+ *   dmi_prepared_view_sizes    elements per view of d_cls / d_lo (W*H) and of d_tileStats
+ *   dmi_prepare_views_device   fills the arrays (d_lo may be NULL); when clsSpareIndex >= 0,
+ *                              d_cls[clsSpareIndex] is set to -1.0f
+ *   dmi_volume_integrate_prepared  like dmi_volume_integrate_device, on prepared views.  d_depths = the
+ *                              UNFILTERED maps (only pixels valid in d_cls are read), or NULL with d_lo given.
+ *                              d_cls[clsSpareIndex] must hold -1.0f and lie within 2^31 floats of every
+ *                              view of the call.
  * Asynchronous on the context's stream. */
 int dmi_prepared_view_sizes(dmi_ctx* ctx, size_t* clsFloatsPerView, size_t* tileFloatsPerView);
 int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
-                             double thresholdBestCost, float* d_cls, long long clsSpareIndex, float* d_tileStats);
-int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const float* d_cls,
-                                  long long clsSpareIndex, const float* d_tileStats, const double* K, const double* RT);
+                             double thresholdBestCost, float* d_cls, int* d_lo, long long clsSpareIndex,
+                             float* d_tileStats);
+int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo,
+                                  const float* d_cls, long long clsSpareIndex, const float* d_tileStats,
+                                  const double* K, const double* RT);
 /* Device address and size in bytes of the slab (valid between begin and the next begin/destroy). */
 int dmi_volume_device_ptr(dmi_ctx* ctx, void** d_ptr, size_t* bytes);
 

@@ -253,6 +253,57 @@ def test_edge_cases_match_oracle(gpu_ctx, oracle, kernel):
     assert np.array_equal(got, want)
 
 
+def test_split_depth_edge_values(gpu_ctx, oracle):
+    """The lossless split depth (float classification + int32 residual) on awkward depths: values next to -1,
+    NaN, +-inf, beyond float range, tiny, negative, many-bit mantissas.  Integration from the split form must
+    equal integration from the double maps, and both the oracle (same discrete decisions)."""
+    import torch
+    grid, rp, W, H, depths, Ks, RTs = edge_scene()
+    depths = depths.copy()
+    rng = np.random.RandomState(11)
+    flat = depths.reshape(-1)
+    special = [np.nextafter(-1.0, 0.0), np.nextafter(-1.0, -2.0), -1.0 - 2.0 ** -25, -1.0 + 2.0 ** -26, np.nan, np.inf, -np.inf,
+               1e300, -1e300, 2.0 ** -70, 0.0, -0.0, 1.0 + 2.0 ** -52, 3.0 - 2.0 ** -51, 2.0 - 2.0 ** -53, np.pi, 1e-30, 5e-324]
+    pos = rng.choice(2 * W * H, size=len(special), replace=False)      # views 0 and 1 (view 2 stays all-invalid)
+    flat[pos] = special
+    want = oracle.tsdf_integrate(grid, rp, W, H, depths, None, 0.0, Ks, RTs, np.zeros(512))
+    ctx = gpu_ctx
+    ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_AUTO)
+    ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
+    got = np.zeros(512)
+    ctx.process_depth_maps(depths, None, 0.0, Ks, RTs, got)
+    nv, npix = 3, W * H
+    dev = torch.device("cuda", 0)
+    d = torch.from_numpy(depths).to(dev)
+    ncls, ntile = ctx.prepared_view_sizes()
+    cls = torch.empty(nv * ncls + 1, dtype=torch.float32, device=dev)
+    lo = torch.empty(nv * npix, dtype=torch.int32, device=dev)
+    tiles = torch.empty(nv * ntile, dtype=torch.float32, device=dev)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        ctx.prepare_views_device(nv, d.data_ptr(), None, 0.0, cls.data_ptr(), nv * npix, tiles.data_ptr(), d_lo=lo.data_ptr())
+        ctx.volume_begin(None, np.float64)
+        ctx.volume_integrate_prepared(nv, None, cls.data_ptr(), nv * npix, tiles.data_ptr(), Ks, RTs, d_lo=lo.data_ptr())
+        split = np.empty(512)
+        ctx.volume_end(split)
+    finally:
+        ctx.set_stream(None)
+    assert np.array_equal(split, got, equal_nan=True)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok] != 0, want[ok] != 0)
+    assert_close(got[ok], want[ok])
+    # the split is exact wherever |d| >= 2^-64 or d == 0 (and keeps inf / NaN)
+    hi32 = cls[:nv * npix].cpu().numpy()
+    e = np.maximum(((hi32.view(np.int32) >> 23) & 0xff) - 127, -64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        rebuilt = hi32.astype(np.float64) + lo.cpu().numpy().astype(np.float64) * np.exp2((e - 53).astype(np.float64))
+    dn = depths.reshape(-1)
+    exact = (hi32 != -1.0) & np.isfinite(dn) & ((np.abs(dn) >= 2.0 ** -64) | (dn == 0)) & (np.abs(dn) < 3e38)
+    assert np.array_equal(rebuilt[exact], dn[exact])
+    assert np.count_nonzero(exact) > 100
+
+
 def test_edge_cases_reference_kernel(oracle):
     """Pins the oracle's device-conversion semantics (NaN, +-inf, saturation) on the reference's own
     kernel running on this GPU: both nvcc builds must agree with the oracle bit for bit."""
@@ -437,3 +488,22 @@ def test_prepared_views_path_is_bit_identical(gpu_ctx):
         ctx.set_stream(None)
     assert cls[-1].item() == -1.0
     assert np.array_equal(out, whole.cpu().numpy())
+    # the same with the LOSSLESS split depth (classification float + int32 residual) instead of the double maps
+    lo = torch.empty(nv * npix, dtype=torch.int32, device=d.device)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        ctx.prepare_views_device(nv, d.data_ptr(), c.data_ptr(), 0.14, cls.data_ptr(), nv * npix, tiles.data_ptr(), d_lo=lo.data_ptr())
+        ctx.volume_begin(None, np.float64)
+        ctx.volume_integrate_prepared(nv, None, cls.data_ptr(), nv * npix, tiles.data_ptr(), K, RT, d_lo=lo.data_ptr())
+        out2 = np.empty(n ** 3)
+        ctx.volume_end(out2)
+    finally:
+        ctx.set_stream(None)
+    assert np.array_equal(out2, out)
+    # and the split itself: hi + lo * 2^(e-53) == depth, bit for bit, on every valid pixel
+    hi = cls[:nv * npix].cpu().numpy().astype(np.float64)
+    e = np.maximum(((cls[:nv * npix].cpu().numpy().view(np.int32) >> 23) & 0xff) - 127, -64)
+    rebuilt = hi + lo.cpu().numpy().astype(np.float64) * np.exp2((e - 53).astype(np.float64))
+    dn = d.cpu().numpy().reshape(-1)
+    valid = hi != -1.0
+    assert valid.any() and np.array_equal(rebuilt[valid], dn[valid])
