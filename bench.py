@@ -59,6 +59,7 @@ def parse_args():
                     help="N>1 view exchange: 'ce' = copy-engine pushes into CUDA-IPC mapped peer buffers (no SMs), 'nccl' = all-gather")
     ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
                     help="N=1 diagnostic: integrate only the z-slab that RANK of WORLD would own (value counts that slab's pairs)")
+    ap.add_argument("--push-streams", type=int, default=4, help="N>1, --exchange ce: streams the peer copies are spread over")
     ap.add_argument("--breakdown", action="store_true", help="N>1: print the comm / compute / gather spans of the last step to stderr")
     ap.add_argument("--cost-model", default="iid", choices=["iid", "coherent"],
                     help="synthetic best-cost maps: independent per pixel (default, the headline workload) or spatially coherent")
@@ -377,7 +378,23 @@ def main():
     # high priority: the all-gather's few CTAs must not queue behind a million integration CTAs
     comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     marks = {}
-    full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
+    full_volume, vol_base, fence2, push_streams = None, None, None, []
+    if world > 1 and peer_ptr is not None:
+        # rank 0's full volume is mapped by every rank, which pushes its finished slab straight into place
+        vol_own = ctx.device_malloc(N ** 3 * 8) if rank == 0 else None
+        hs = [ctx.ipc_get_handle(vol_own) if rank == 0 else None]
+        dist.broadcast_object_list(hs, src=0)
+        vol_base = vol_own if rank == 0 else ctx.ipc_open_handle(hs[0])
+        if rank == 0:
+            class _Vol:
+                pass
+            hv = _Vol()
+            hv.__cuda_array_interface__ = {"shape": (N ** 3,), "typestr": "<f8", "data": (vol_own, False), "version": 3}
+            full_volume = torch.as_tensor(hv, device=dev)
+        fence2 = torch.zeros(1, dtype=torch.float32, device=dev)
+        push_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(min(args.push_streams, world - 1))]
+    elif world > 1 and rank == 0:
+        full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev)
 
     def slab_tensor():
         """The context's slab (device memory owned by libdmi_b200) as a tensor, without copying."""
@@ -445,12 +462,21 @@ def main():
                         c_rel = (cls_off[g0] + (a - g0) * ncls) * 4
                         ctx.prepare_views_device(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
                                                  cls_ptr + c_rel, -1, tile_ptr + a * ntile * 4, d_lo=own_ptr + a * npix * 4)
+                        prepared = torch.cuda.Event()
+                        prepared.record(comm_stream)
                         for r in range(1, world):      # staggered order: every link busy, no hot receiver
                             dst = (rank + r) % world
                             base = peer_ptr[dst]
+                            ps = push_streams[r % len(push_streams)]      # several copies in flight at once
+                            ps.wait_event(prepared)
+                            ctx.set_stream(ps.cuda_stream)
                             ctx.memcpy_device_async(base + a * npix * 4, own_ptr + a * npix * 4, n * npix * 4)
                             ctx.memcpy_device_async(base + depth_bytes + c_rel, cls_ptr + c_rel, n * ncls * 4)
                             ctx.memcpy_device_async(base + depth_bytes + cls_bytes + a * ntile * 4, tile_ptr + a * ntile * 4, n * ntile * 4)
+                        for ps in push_streams:
+                            pushed = torch.cuda.Event()
+                            pushed.record(ps)
+                            comm_stream.wait_event(pushed)
                         ctx.set_stream(cur.cuda_stream)
                         off += n
                     dist.all_reduce(fence)      # all shares of this group have landed everywhere
@@ -476,7 +502,13 @@ def main():
         # the finished slabs are gathered once (for contouring on rank 0); slabs may differ by one plane
         if args.breakdown:
             marks["compute_done"].record(cur)
-        D.gather_slabs(dist, slab_tensor(), full_volume, N * N, N, rank, world)
+        if vol_base is not None:
+            ptr, nbytes = ctx.volume_device_ptr()
+            if nbytes:
+                ctx.memcpy_device_async(vol_base + sharding.slab_range(N, rank, world)[0] * N * N * 8, ptr, nbytes)
+            dist.all_reduce(fence2)              # every slab has landed in rank 0's volume
+        else:
+            D.gather_slabs(dist, slab_tensor(), full_volume, N * N, N, rank, world)
         if args.breakdown:
             marks["gather_done"].record(cur)
 
