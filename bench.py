@@ -55,8 +55,11 @@ def parse_args():
     ap.add_argument("--no-coloration", action="store_true")
     ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
     ap.add_argument("--group", type=int, default=128, help="views per all-gather group (N>1)")
-    ap.add_argument("--exchange", default="ce", choices=["ce", "nccl"],
-                    help="N>1 view exchange: 'ce' = copy-engine pushes into CUDA-IPC mapped peer buffers (no SMs), 'nccl' = all-gather")
+    ap.add_argument("--exchange", default="ce", choices=["ce", "fused", "nccl"],
+                    help="N>1 view exchange: 'ce' = owner-side preparation + copy-engine pushes into CUDA-IPC mapped peer buffers (no SMs; "
+                         "the fastest measured), 'fused' = the preparation kernel stores its outputs straight into every rank's mapped "
+                         "buffers over NVLink (measured slower: SM stores reach ~230 GB/s and hold SMs the integration wants), "
+                         "'nccl' = all-gather of the double maps + preparation on every rank")
     ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
                     help="N=1 diagnostic: integrate only the z-slab that RANK of WORLD would own (value counts that slab's pairs)")
     ap.add_argument("--push-streams", type=int, default=4, help="N>1, --exchange ce: streams the peer copies are spread over")
@@ -258,6 +261,8 @@ def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+EXCHANGE_TEXT = {"fused": "prepared by their owner straight into every rank's buffers: stores over NVLink from the preparation kernel",
+                 "ce": "copy-engine pushes over CUDA IPC", "nccl": "NCCL all-gather"}
 _JSON_OUT = None
 
 
@@ -327,7 +332,7 @@ def main():
     noise = 0.25 * float(grid.spacing.max())
     all_depths, peer_ptr, own_ptr, fence = None, None, None, None
     cls_ptr = tile_ptr = None
-    if world > 1 and args.exchange == "ce":
+    if world > 1 and args.exchange in ("ce", "fused"):
         # the resident view buffers are allocated by the library (plain cudaMalloc) so that every rank can map
         # every other rank's buffers through CUDA IPC and PUSH its share with the copy engines over NVLink.
         # One allocation: [residual i32 V*npix][classification f32, per group: n*npix + 4 spare][tile statistics f32];
@@ -337,8 +342,8 @@ def main():
         cls_off, acc = {}, 0
         for (g0, g1) in groups:
             cls_off[g0] = acc
-            acc += (g1 - g0) * ncls + 4
-        depth_bytes = V * npix * 4
+            acc += ((g1 - g0) * ncls + 8 + 7) // 8 * 8      # spare slot; groups stay 32-byte aligned
+        depth_bytes = (V * npix * 4 + 255) // 256 * 256
         cls_bytes = (acc * 4 + 255) // 256 * 256
         own_ptr = ctx.device_malloc(depth_bytes + cls_bytes + V * ntile * 4)
         cls_ptr, tile_ptr = own_ptr + depth_bytes, own_ptr + depth_bytes + cls_bytes
@@ -353,7 +358,7 @@ def main():
         peer_ptr = [own_ptr if r == rank else ctx.ipc_open_handle(handles[r]) for r in range(world)]
         fence = torch.zeros(1, dtype=torch.float32, device=dev)
         # the spare "invalid" slot after each group's classification images is written once, locally
-        minus1 = torch.full((4,), -1.0, dtype=torch.float32, device=dev)
+        minus1 = torch.full((4,), -1.0, dtype=torch.float32, device=dev)      # (the slot right behind the group's images)
         for (g0, g1) in groups:
             ctx.memcpy_device_async(cls_ptr + (cls_off[g0] + (g1 - g0) * ncls) * 4, minus1.data_ptr(), 16)
         ctx.synchronize()
@@ -460,6 +465,19 @@ def main():
                         # and pushes depth, classification and pyramid to every rank, itself included
                         ctx.set_stream(comm_stream.cuda_stream)
                         c_rel = (cls_off[g0] + (a - g0) * ncls) * 4
+                        if args.exchange == "fused":
+                            order = [rank] + [(rank + r) % world for r in range(1, world)]      # local first
+                            ctx.prepare_views_multi(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
+                                                    [peer_ptr[q] + depth_bytes + c_rel for q in order], -1,
+                                                    [peer_ptr[q] + depth_bytes + cls_bytes + a * ntile * 4 for q in order],
+                                                    d_lo=[peer_ptr[q] + a * npix * 4 for q in order])
+                            ctx.set_stream(cur.cuda_stream)
+                            off += n
+                            dist.all_reduce(fence)
+                            ev = torch.cuda.Event()
+                            ev.record(comm_stream)
+                            events.append(ev)
+                            continue
                         ctx.prepare_views_device(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
                                                  cls_ptr + c_rel, -1, tile_ptr + a * ntile * 4, d_lo=own_ptr + a * npix * 4)
                         prepared = torch.cuda.Event()
@@ -634,7 +652,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H}, best-cost threshold {THRESH}, f64 volume",
-                       "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views exchanged in groups of {G} ({'copy-engine pushes over CUDA IPC' if args.exchange == 'ce' else 'NCCL all-gather'})" if world > 1 else ""),
+                       "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views exchanged in groups of {G} ({EXCHANGE_TEXT[args.exchange]})" if world > 1 else ""),
                        "l2": "inputs (%.1f GB per step) exceed L2; no flush needed" % (algorithmic_bytes(N, V, W, H) / 1e9),
                        "kernel": args.kernel, "cull": args.cull, "cost_model": args.cost_model},
             "roofline": roofline, "gpu_launches": launches, "clocks": clocks,

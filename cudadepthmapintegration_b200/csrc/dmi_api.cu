@@ -526,6 +526,31 @@ int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, c
   return DMI_OK;
 }
 
+int dmi_prepare_views_multi(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
+                            double thresholdBestCost, int nDst, float* const* d_cls, int* const* d_lo,
+                            long long clsSpareIndex, float* const* d_tileStats)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
+  DMI_REQUIRE(d_depths && d_cls && d_tileStats, "null argument");
+  DMI_REQUIRE(nDst >= 1 && nDst <= dmi::kMaxPrepareDst, "nDst must be between 1 and 8");
+  dmi::PrepareDst dst = {};
+  dst.n = nDst;
+  uintptr_t bits = 0;
+  for (int r = 0; r < nDst; r++)
+  {
+    DMI_REQUIRE(d_cls[r] && d_tileStats[r] && (!d_lo || d_lo[r]), "null destination");
+    dst.cls[r] = d_cls[r]; dst.lo[r] = d_lo ? d_lo[r] : nullptr; dst.tiles[r] = d_tileStats[r];
+    bits |= reinterpret_cast<uintptr_t>(dst.cls[r]) | reinterpret_cast<uintptr_t>(dst.lo[r]);
+  }
+  dst.aligned = (bits & 31) == 0;
+  DMI_CK(cudaSetDevice(ctx->device));
+  DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, dst, clsSpareIndex, ctx->stream));
+  ctx->total_launches++;
+  return DMI_OK;
+}
+
 int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo, const float* d_cls,
                                   long long clsSpareIndex, const float* d_tileStats, const double* K, const double* RT)
 {

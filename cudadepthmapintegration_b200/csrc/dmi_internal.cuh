@@ -96,6 +96,18 @@ struct TilePyramid
 };
 TilePyramid tile_pyramid_layout(int W, int H);
 // clsSpare: index (relative to d_cls) of a float that is set to -1.0f for the rejected voxels' gathers; < 0 = none
+// Destinations of the view preparation: dst 0 is local; the others may be peer GPUs' buffers (same layout).
+constexpr int kMaxPrepareDst = 8;
+struct PrepareDst
+{
+  int n;
+  int aligned;                    // every cls / lo pointer is 32-byte aligned
+  float* cls[kMaxPrepareDst];
+  int* lo[kMaxPrepareDst];        // all null or all set
+  float* tiles[kMaxPrepareDst];
+};
+cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
+                                 const PrepareDst& dst, long long clsSpare, cudaStream_t s);
 // d_lo (may be null): residual image of the lossless split depth = (cls, lo), see split_encode
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
                                  float* d_cls, int* d_lo, long long clsSpare, float* d_tileDmax, cudaStream_t s);

@@ -712,12 +712,16 @@ TilePyramid tile_pyramid_layout(int W, int H)
   return p;
 }
 
+// Every output is written to ALL destinations of `dst` (dst 0 is local, the others may be peer GPUs' mapped
+// buffers: plain stores over NVLink, 32-byte vectors when the rows allow it) -- view preparation fused with
+// its all-gather.
 __global__ void __launch_bounds__(256)
 prepare_views_kernel(const double* __restrict__ depths, const double* __restrict__ cost, double thr,
-                     int nViews, int W, int H, int TW, int TH, int perView, int minOff, float* __restrict__ cls,
-                     int* __restrict__ lo, long long clsSpare, float* __restrict__ tileStats)
+                     int nViews, int W, int H, int TW, int TH, int perView, int minOff,
+                     const __grid_constant__ PrepareDst dst, long long clsSpare)
 {
-  if (blockIdx.x == 0 && threadIdx.x == 0 && clsSpare >= 0) cls[clsSpare] = -1.0f;   // the spare slot, see phase B
+  if (blockIdx.x == 0 && threadIdx.x == 0 && clsSpare >= 0)
+    for (int r = 0; r < dst.n; r++) dst.cls[r][clsSpare] = -1.0f;                     // the spare slot, see phase B
   const int lane = threadIdx.x & 31;
   const int BW = (TW + 1) / 2, BH = (TH + 1) / 2;             // blocks of 2 x 2 tiles
   const size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -728,20 +732,23 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
   const int by = t / BW, bx = t % BW;
   const int row = by * 16 + (lane >> 1), col = bx * 16 + (lane & 1) * 8;
   float dmax = -INFINITY, dmin = INFINITY;
-  if (row < H)
+  if (row < H && col < W)
   {
-    const size_t base = (size_t)v * W * H + (size_t)row * W;
+    const size_t base = (size_t)v * W * H + (size_t)row * W + col;
+    float f8[8];
+    int l8[8];
+    const bool wantLo = dst.lo[0] != nullptr;
 #pragma unroll
     for (int q = 0; q < 8; q++)
     {
+      f8[q] = -1.0f; l8[q] = 0;
       if (col + q < W)
       {
-        const double d = __ldg(depths + base + col + q);
-        const bool invalid = (d == -1.0) || (cost && __ldg(cost + base + col + q) > thr);
-        float f = -1.0f;
+        const double d = __ldg(depths + base + q);
+        const bool invalid = (d == -1.0) || (cost && __ldg(cost + base + q) > thr);
         if (!invalid)
         {
-          f = __double2float_rn(d);
+          float f = __double2float_rn(d);
           if (f == -1.0f) f = (d < -1.0) ? -1.00000012f : -0.99999994f;       // never -1.0f on a valid pixel
           // tile maximum, rounded up; NaN poisons the tile (+inf: never culled as "far behind")
           float up = f;
@@ -751,10 +758,32 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
           float dn = f;
           if ((double)dn > d) dn = __int_as_float(__float_as_int(dn) + (dn > 0.f ? -1 : 1));
           dmin = (d != d) ? -INFINITY : fminf(dmin, dn);
+          f8[q] = f;
+          if (wantLo) l8[q] = split_encode(d, f);
         }
         else dmin = -INFINITY;
-        cls[base + col + q] = f;
-        if (lo) lo[base + col + q] = invalid ? 0 : split_encode(d, f);
+      }
+    }
+    const bool vec = ((W & 7) == 0) && dst.aligned;            // whole 32-byte groups, 32-byte aligned rows
+    for (int r = 0; r < dst.n; r++)
+    {
+      float* c = dst.cls[r] + base;
+      int* l = wantLo ? dst.lo[r] + base : nullptr;
+      if (vec)
+      {
+        reinterpret_cast<float4*>(c)[0] = make_float4(f8[0], f8[1], f8[2], f8[3]);
+        reinterpret_cast<float4*>(c)[1] = make_float4(f8[4], f8[5], f8[6], f8[7]);
+        if (l)
+        {
+          reinterpret_cast<int4*>(l)[0] = make_int4(l8[0], l8[1], l8[2], l8[3]);
+          reinterpret_cast<int4*>(l)[1] = make_int4(l8[4], l8[5], l8[6], l8[7]);
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (col + q < W) { c[q] = f8[q]; if (l) l[q] = l8[q]; }
       }
     }
   }
@@ -768,15 +797,15 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
   const int tx = bx * 2 + (lane & 1), ty = by * 2 + (lane >> 4);
   if ((lane & 14) == 0 && tx < TW && ty < TH)
   {
-    float* o = tileStats + (size_t)v * perView + ty * TW + tx;
-    o[0] = dmax;
-    o[minOff] = dmin;
+    const size_t o = (size_t)v * perView + ty * TW + tx;
+    for (int r = 0; r < dst.n; r++) { dst.tiles[r][o] = dmax; dst.tiles[r][o + minOff] = dmin; }
   }
 }
 
-// level l from level l-1: windows of 2^l tiles = four windows of 2^(l-1) tiles, h = 2^(l-1) apart (clipped)
+// level l from level l-1: windows of 2^l tiles = four windows of 2^(l-1) tiles, h = 2^(l-1) apart (clipped);
+// read from the local copy, written everywhere
 __global__ void __launch_bounds__(256)
-tile_level_kernel(float* __restrict__ tiles, int nViews, int perView, int minOff, int tw, int th, int l)
+tile_level_kernel(const __grid_constant__ PrepareDst dst, int nViews, int perView, int minOff, int tw, int th, int l)
 {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t per = (size_t)tw * th;
@@ -784,36 +813,48 @@ tile_level_kernel(float* __restrict__ tiles, int nViews, int perView, int minOff
   const int v = (int)(t / per), q = (int)(t % per);
   const int y = q / tw, x = q % tw, h = 1 << (l - 1);
   const int x1 = min(x + h, tw - 1), y1 = min(y + h, th - 1);
-  const float* src = tiles + (size_t)v * perView + (size_t)(l - 1) * per;
-  float* dst = tiles + (size_t)v * perView + (size_t)l * per;
-  dst[q] = fmaxf(fmaxf(src[y * tw + x], src[y * tw + x1]), fmaxf(src[y1 * tw + x], src[y1 * tw + x1]));
+  const float* src = dst.tiles[0] + (size_t)v * perView + (size_t)(l - 1) * per;
+  const float mx = fmaxf(fmaxf(src[y * tw + x], src[y * tw + x1]), fmaxf(src[y1 * tw + x], src[y1 * tw + x1]));
   const float* srn = src + minOff;
-  dst[minOff + q] = fminf(fminf(srn[y * tw + x], srn[y * tw + x1]), fminf(srn[y1 * tw + x], srn[y1 * tw + x1]));
+  const float mn = fminf(fminf(srn[y * tw + x], srn[y * tw + x1]), fminf(srn[y1 * tw + x], srn[y1 * tw + x1]));
+  const size_t o = (size_t)v * perView + (size_t)l * per + q;
+  for (int r = 0; r < dst.n; r++) { dst.tiles[r][o] = mx; dst.tiles[r][o + minOff] = mn; }
 }
 
 // flag = 1.0f when some tile of the view is fully valid (its min statistic is finite or +inf)
-__global__ void __launch_bounds__(256) view_flag_kernel(float* __restrict__ tiles, int perView, int minOff, int flagOff, int n0)
+__global__ void __launch_bounds__(256) view_flag_kernel(const __grid_constant__ PrepareDst dst, int perView, int minOff, int flagOff, int n0)
 {
-  const float* t = tiles + (size_t)blockIdx.x * perView + minOff;
+  const float* t = dst.tiles[0] + (size_t)blockIdx.x * perView + minOff;
   int any = 0;
   for (int q = threadIdx.x; q < n0; q += blockDim.x) any |= (t[q] > -INFINITY) ? 1 : 0;
   any = __syncthreads_or(any);
-  if (threadIdx.x == 0) tiles[(size_t)blockIdx.x * perView + flagOff] = any ? 1.0f : 0.0f;
+  if (threadIdx.x == 0)
+    for (int r = 0; r < dst.n; r++) dst.tiles[r][(size_t)blockIdx.x * perView + flagOff] = any ? 1.0f : 0.0f;
+}
+
+cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
+                                 const PrepareDst& dst, long long clsSpare, cudaStream_t s)
+{
+  const TilePyramid p = tile_pyramid_layout(W, H);
+  const size_t blocks2x2 = (size_t)((p.tw + 1) / 2) * ((p.th + 1) / 2) * nViews;
+  if (blocks2x2 == 0 || dst.n <= 0) return cudaSuccess;
+  prepare_views_kernel<<<(unsigned)((blocks2x2 + 7) / 8), 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw, p.th, p.perView,
+                                                                       p.minOff, dst, clsSpare);
+  const size_t n = (size_t)p.tw * p.th * nViews;
+  for (int l = 1; l < p.nLevels; l++)
+    tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, nViews, p.perView, p.minOff, p.tw, p.th, l);
+  view_flag_kernel<<<nViews, 256, 0, s>>>(dst, p.perView, p.minOff, p.flagOff, p.tw * p.th);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
                                  float* d_cls, int* d_lo, long long clsSpare, float* d_tileStats, cudaStream_t s)
 {
-  const TilePyramid p = tile_pyramid_layout(W, H);
-  const size_t blocks2x2 = (size_t)((p.tw + 1) / 2) * ((p.th + 1) / 2) * nViews;
-  if (blocks2x2 == 0) return cudaSuccess;
-  prepare_views_kernel<<<(unsigned)((blocks2x2 + 7) / 8), 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw, p.th, p.perView,
-                                                                       p.minOff, d_cls, d_lo, clsSpare, d_tileStats);
-  const size_t n = (size_t)p.tw * p.th * nViews;
-  for (int l = 1; l < p.nLevels; l++)
-    tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_tileStats, nViews, p.perView, p.minOff, p.tw, p.th, l);
-  view_flag_kernel<<<nViews, 256, 0, s>>>(d_tileStats, p.perView, p.minOff, p.flagOff, p.tw * p.th);
-  return cudaGetLastError();
+  PrepareDst dst = {};
+  dst.n = 1;
+  dst.cls[0] = d_cls; dst.lo[0] = d_lo; dst.tiles[0] = d_tileStats;
+  dst.aligned = ((reinterpret_cast<uintptr_t>(d_cls) | reinterpret_cast<uintptr_t>(d_lo)) & 31) == 0;
+  return launch_prepare_views(d_depths, d_cost, thr, nViews, W, H, dst, clsSpare, s);
 }
 
 // ---- host side: composition of the per-view affine rows ----------------------------------------

@@ -14,17 +14,22 @@ from . import sharding
 def view_groups(n_views: int, group: int, world: int, ramp: bool = True):
     """[(g0, g1)] consecutive groups of views; every group size is a multiple of the world size.  With
     `ramp` the first groups are smaller (G/4, G/4, G/2), so that integration starts after a short first
-    exchange instead of waiting for a full group."""
+    exchange instead of waiting for a full group, and so are the last ones (G/2, G/4, G/4): what is left
+    to integrate once the last views have arrived is a quarter group, not a whole one."""
     g = max(world, (max(group, 1) // world) * world)
-    sizes = []
-    if ramp and world > 1:
-        for f in (4, 4, 2):
-            q = max(world, (g // f // world) * world)
-            if q < g:
-                sizes.append(q)
+
+    def part(f):
+        return max(world, (g // f // world) * world)
+    head = [q for q in (part(4), part(4), part(2)) if q < g] if ramp and world > 1 else []
+    tail = [q for q in (part(2), part(4), part(4)) if q < g] if ramp and world > 1 else []
     out, g0, i = [], 0, 0
     while g0 < n_views:
-        q = sizes[i] if i < len(sizes) else g
+        if i < len(head):
+            q = head[i]
+        elif tail and n_views - g0 <= sum(tail):
+            q = tail.pop(0)
+        else:
+            q = g
         out.append((g0, min(n_views, g0 + q)))
         g0 += q
         i += 1

@@ -162,6 +162,17 @@ class Context:
                                                     _ptr(int(d_cls)), _ptr(int(d_lo)) if d_lo else None,
                                                     int(cls_spare_index), _ptr(int(d_tiles))))
 
+    def prepare_views_multi(self, n_views: int, d_depths: int, d_best_cost: int | None, threshold, d_cls, cls_spare_index: int,
+                            d_tiles, d_lo=None):
+        """prepare_views_device fused with its all-gather: d_cls / d_tiles / d_lo are lists of device addresses
+        (entry 0 local, the others may be peer-mapped buffers); every output is stored to all of them."""
+        n = len(d_cls)
+        arr = lambda xs: (C.c_void_p * n)(*[int(x) for x in xs])
+        self._ck(self._lib.dmi_prepare_views_multi(self._h, int(n_views), _ptr(int(d_depths)),
+                                                   _ptr(int(d_best_cost)) if d_best_cost else None, float(threshold), n,
+                                                   arr(d_cls), arr(d_lo) if d_lo is not None else None,
+                                                   int(cls_spare_index), arr(d_tiles)))
+
     def volume_integrate_prepared(self, n_views: int, d_depths: int | None, d_cls: int, cls_spare_index: int, d_tiles: int,
                                   K, RT, d_lo: int | None = None):
         """Exactly one of d_depths (double maps) / d_lo (residual image of the split depth) is needed."""

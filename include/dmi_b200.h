@@ -143,6 +143,12 @@ int dmi_prepared_view_sizes(dmi_ctx* ctx, size_t* clsFloatsPerView, size_t* tile
 int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
                              double thresholdBestCost, float* d_cls, int* d_lo, long long clsSpareIndex,
                              float* d_tileStats);
+/* dmi_prepare_views_device fused with its all-gather: every output is stored into nDst (<= 8) sets of
+ * arrays; set 0 must be local to the context's device (the level passes read it back), the others may be
+ * peer GPUs' buffers opened with dmi_ipc_open_handle (plain stores over NVLink).  d_lo may be NULL. */
+int dmi_prepare_views_multi(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
+                            double thresholdBestCost, int nDst, float* const* d_cls, int* const* d_lo,
+                            long long clsSpareIndex, float* const* d_tileStats);
 int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo,
                                   const float* d_cls, long long clsSpareIndex, const float* d_tileStats,
                                   const double* K, const double* RT);
