@@ -619,7 +619,7 @@ def main():
         all_pairs_tflops = FLOPS_PER_UNIT * k_units / k_sec / 1e12
         evaluated = 1.0
         if tiers and tiers["brick_views"] > 0:
-            evaluated = 1.0 - (tiers["culled_brick_views"] + tiers["uniform_front"]) / tiers["brick_views"]
+            evaluated = tiers["units"] / (units / world)          # rank 0's slab
         ach = all_pairs_tflops * evaluated
         alg_bytes = algorithmic_bytes(N, V, W, H) / world * args.steps
         roofline = {
@@ -631,7 +631,7 @@ def main():
             "peak_source": "FFMA issue-rate microbenchmark run in this process (dmi_measure_fp_peak); MEASURED_PEAKS.json has no FP32/FP64 vector peak",
             "binding_resource": "instruction issue (compares, rounding, address arithmetic, one gather per pair): see profiles/ for smsp__issue_active",
             "evaluated_fraction_of_pairs": evaluated,
-            "free_space_fraction_of_pairs": (tiers["uniform_front"] / tiers["brick_views"]) if tiers and tiers["brick_views"] else None,
+            "free_space_fraction_of_pairs": (tiers["uniform_front"] / (units / world)) if tiers else None,
             "all_pairs": {"achieved": all_pairs_tflops, "frac_fp32": all_pairs_tflops / fp32_peak, "frac_fp64": all_pairs_tflops / fp64_peak,
                           "note": "all N^3*V pairs counted as SURVEY.md 8d asks; exceeds the FMA roofline because most pairs are proven to contribute nothing without being evaluated"},
             "fp64_basis": {"peak": fp64_peak, "frac": ach / fp64_peak, "peak_source": "DFMA microbenchmark, this process"},

@@ -71,7 +71,7 @@ struct FastChunk
 struct FastCounters               // optional diagnostics (device memory, may be null)
 {
   unsigned long long t1_certified, t2_entered, t3_entered, delta_guard, units, culled, near_band, brick_views;
-  unsigned long long uniform_front;     // (brick, view) pairs settled by one add per voxel, see eval_box
+  unsigned long long uniform_front;     // voxel*views settled brick-wide by one add per voxel, see eval_box
   unsigned long long reserved[7];       // [0] far in front, [1] far behind, [2] invalid pixel (voxel*views, FP32 phase C)
 };
 
@@ -117,7 +117,7 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
                              ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
                              FastCounters* d_counters, cudaStream_t s);
-size_t tsdf_fast_mask_bytes(const GridParams& g);   // size of d_maskScratch (one 64-bit view mask per supertile)
+size_t tsdf_fast_mask_bytes(const GridParams& g);   // size of d_maskScratch: per supertile a 64-bit view mask + a list entry, + work counters
 void compose_fast_view(const GridParams& g, const double* K16, const double* RT16, int cxc, int cyc, ViewFast* out);
 void fill_fast_chunk_constants(const GridParams& g, FastChunk* c);
 

@@ -302,23 +302,45 @@ __device__ __forceinline__ int nth_set_bit64(unsigned lo, unsigned hi, int n)
   return n < nlo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - nlo + 1);
 }
 
+// Ordered list of the supertiles some view of the chunk may touch (all of them when useMasks == 0), and the
+// work counter of the persistent integration kernel: work[0] = number of active supertiles, work[1] = 0.
+__global__ void __launch_bounds__(1024)
+compact_supertiles_kernel(const unsigned* __restrict__ masks, int nst, int useMasks, int* __restrict__ list, int* __restrict__ work)
+{
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nst; b0 += 1024)
+  {
+    const int st = b0 + threadIdx.x;
+    const bool act = st < nst && (!useMasks || (masks[2 * st] | masks[2 * st + 1]) != 0u);
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    int pos = s_base + __popc(bal & ((1u << lane) - 1u));
+    for (int q = 0; q < w; q++) pos += s_warp[q];
+    if (act) list[pos] = st;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 32; q++) t += s_warp[q]; s_base += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { work[0] = s_base; work[1] = 0; }
+}
+
+// One brick (st = supertile, rr = brick within it) against the chunk's views.  All threads of the CTA call it.
 // SPLIT: the double depths are not resident; the band and the exact tier rebuild them from the classification
 // image and the residual image `lo` (split_decode), bit for bit.
 template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
-__global__ void __launch_bounds__(FT)
-tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
-                 const double* __restrict__ depths, const int* __restrict__ lo, const float* __restrict__ cls,
-                 const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
-                 long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
-                 T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters)
+__device__ __forceinline__ void
+fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ depths, const int* __restrict__ lo,
+           const float* __restrict__ cls, const float* __restrict__ tileDmax, const TilePyramid& pyr, int cull,
+           long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
+           T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters, unsigned st, unsigned rr,
+           ViewSm* s_view, int* s_cnt)
 {
-  static_assert(kFastChunk <= FT, "one pre-pass thread per view");
-  __shared__ ViewSm s_view[kFastChunk];
-  __shared__ int s_cnt[FT / 32];
-
   // ---- brick decode (CTA-uniform)
-  constexpr unsigned per = FSI * FSJ * FSK;
-  const unsigned st = blockIdx.x / per, rr = blockIdx.x % per;
   const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ;
   const int bi = (st % nsi) * FSI + rr % FSI;
   const int bj = ((st / nsi) % nsj) * FSJ + (rr / FSI) % FSJ;
@@ -383,11 +405,8 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   __syncthreads();
   if (COUNT && counters && threadIdx.x == 0)
   {
-    int nf = 0;
-    for (int q = 0; q < nsurv; q++) nf += s_view[q].pad;
     atomicAdd(&counters->culled, (unsigned long long)(c.n - nsurv));
     atomicAdd(&counters->brick_views, (unsigned long long)c.n);
-    atomicAdd(&counters->uniform_front, (unsigned long long)nf);
   }
 
   const int li = (w & 1) * 8 + (lane & 7), lj = (w >> 1) * 4 + (lane >> 3);
@@ -601,9 +620,10 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   {
     // one atomic per warp and counter (the lanes that returned early above are simply absent)
     const unsigned act = __activemask();
-    unsigned long long vals[9] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)FM * (nsurv - n_uf), n_front, n_behind, n_inv};
+    unsigned long long vals[10] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)nk * (nsurv - n_uf), n_front, n_behind, n_inv,
+                                   (unsigned long long)nk * n_uf};
 #pragma unroll
-    for (int q = 0; q < 9; q++)
+    for (int q = 0; q < 10; q++)
     {
       unsigned long long x = vals[q];
       for (int o = 16; o > 0; o >>= 1)
@@ -624,7 +644,40 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
       atomicAdd(&counters->reserved[0], vals[6]);
       atomicAdd(&counters->reserved[1], vals[7]);
       atomicAdd(&counters->reserved[2], vals[8]);
+      atomicAdd(&counters->uniform_front, vals[9]);
     }
+  }
+}
+
+// Persistent kernel: as many CTAs as fit the GPU; each takes the next brick of the next ACTIVE supertile from a
+// global counter until none is left (a launch over all bricks would spend ~2 ns on each of the many bricks
+// no view of the chunk can touch).  5 CTAs per SM (96 registers, ~130 bytes of spills in the rare tiers):
+// measured on config5, ms per step at 3 / 4 / 5 / 6 CTAs per SM = 292 / 254 / 238 / 246 -- the gathers'
+// latency wants warps more than the loop wants registers.
+template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
+__global__ void __launch_bounds__(FT, 5)
+tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
+                 const double* __restrict__ depths, const int* __restrict__ lo, const float* __restrict__ cls,
+                 const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
+                 long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
+                 const int* __restrict__ stlist, int* __restrict__ work,
+                 T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters)
+{
+  static_assert(kFastChunk <= FT, "one pre-pass thread per view");
+  __shared__ ViewSm s_view[kFastChunk];
+  __shared__ int s_cnt[FT / 32];
+  __shared__ int s_item;
+  constexpr int per = FSI * FSJ * FSK;
+  const int nItems = work[0] * per;
+  for (;;)
+  {
+    __syncthreads();                                          // the previous brick is done with shared memory
+    if (threadIdx.x == 0) s_item = atomicAdd(work + 1, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= nItems) break;
+    fast_brick<T, PINHOLE, COUNT, SPLIT>(g, c, depths, lo, cls, tileDmax, pyr, cull, clsSpare, gviews, stmasks, vol, nbi, nbj, nbk,
+                                         counters, (unsigned)__ldg(stlist + item / per), (unsigned)(item % per), s_view, s_cnt);
   }
 }
 
@@ -641,21 +694,32 @@ __global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant_
   if ((int)threadIdx.x < c.n) dst[threadIdx.x].pad[0] = tiles[(size_t)threadIdx.x * perView + flagOff];
 }
 
+// CTAs that are resident at once on this device for `kernel` (never more than there are bricks)
+static unsigned persistent_grid(const void* kernel, unsigned bricks)
+{
+  int dev = 0, sms = 0, perSm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, FT, 0);
+  return std::max(1u, std::min(bricks, (unsigned)(std::max(sms, 1) * std::max(perSm, 1))));
+}
+
 template <typename T, bool PINHOLE>
 static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                            const float* d_cls, const float* d_tileDmax, const TilePyramid& pyr, bool cull,
                            long long clsSpare, const ViewFast* d_views, unsigned* d_masks, T* d_vol, int nbi, int nbj,
                            int nbk, FastCounters* d_counters, cudaStream_t s)
 {
-  if (cull && d_masks)
-  {
-    const int nst = (int)(grid / (FSI * FSJ * FSK));
+  const int nst = (int)(grid / (FSI * FSJ * FSK));
+  if (cull)
     supertile_cull_kernel<PINHOLE><<<(nst + 3) / 4, 256, 0, s>>>(g, c, d_tileDmax, pyr, d_views, nbi, nbj, nbk, d_masks, nst);
-  }
-  const unsigned* masks = (cull && d_masks) ? d_masks : nullptr;
+  const unsigned* masks = cull ? d_masks : nullptr;
+  int* list = reinterpret_cast<int*>(d_masks + 2 * (size_t)nst);
+  int* work = list + nst;
+  compact_supertiles_kernel<<<1, 1024, 0, s>>>(d_masks, nst, cull ? 1 : 0, list, work);
 #define DMI_LAUNCH_FAST(COUNT, SPLIT, CNT)                                                                         \
-  tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT><<<grid, FT, 0, s>>>(g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull ? 1 : 0, \
-                                                                 clsSpare, d_views, masks, d_vol, nbi, nbj, nbk, CNT)
+  tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT><<<persistent_grid((const void*)tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT>, grid), FT, 0, s>>>( \
+      g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, list, work, d_vol, nbi, nbj, nbk, CNT)
   if (d_counters) { if (d_depths) DMI_LAUNCH_FAST(true, false, d_counters); else DMI_LAUNCH_FAST(true, true, d_counters); }
   else { if (d_depths) DMI_LAUNCH_FAST(false, false, nullptr); else DMI_LAUNCH_FAST(false, true, nullptr); }
 #undef DMI_LAUNCH_FAST
@@ -665,7 +729,7 @@ size_t tsdf_fast_mask_bytes(const GridParams& g)
 {
   const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
   const size_t nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
-  return std::max<size_t>(8, nsi * nsj * nsk * 8);
+  return nsi * nsj * nsk * 12 + 16;       // masks (2 words), the active list (1 word) per supertile + the work counters
 }
 
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,

@@ -167,8 +167,9 @@ int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
 /* Diagnostics of the certified fast path (DMI_OPT_TIER_COUNTERS = 1): out[0] voxel*views certified by
  * the FP32 tier, [1] sent to the FP64 tier, [2] sent to the exact tier, [3] exact because |diff| was
  * within the guard band of Delta, [4] voxel*views evaluated one by one after culling, [5] (brick, view)
- * pairs culled, [6] voxel*views in the FP64 band around the surface, [7] (brick, view) pairs seen,
- * [8] (brick, view) pairs settled brick-wide as free space in front of the surface (one add per voxel),
+ * pairs culled and [7] seen by the bricks the kernel visited (supertiles no view can touch are not visited),
+ * [6] voxel*views in the FP64 band around the surface,
+ * [8] voxel*views settled brick-wide as free space in front of the surface (one add per voxel),
  * [9] voxel*views classified far in front of the depth, [10] far behind it, [11] on an invalid pixel
  * (or rejected: behind the camera / outside the image) by the FP32 phase, [12..15] reserved (0).  Reading resets the counters. */
 int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[16]);
