@@ -62,6 +62,7 @@ def parse_args():
                          "'nccl' = all-gather of the double maps + preparation on every rank")
     ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
                     help="N=1 diagnostic: integrate only the z-slab that RANK of WORLD would own (value counts that slab's pairs)")
+    ap.add_argument("--quota", type=int, default=0, help="bricks per CTA of the integration kernel (0: 32 at N=1, 8 at N>1)")
     ap.add_argument("--push-streams", type=int, default=4, help="N>1, --exchange ce: streams the peer copies are spread over")
     ap.add_argument("--breakdown", action="store_true", help="N>1: print the comm / compute / gather spans of the last step to stderr")
     ap.add_argument("--cost-model", default="iid", choices=["iid", "coherent"],
@@ -317,6 +318,8 @@ def main():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_EXACT if args.kernel == "exact" else _lib.DMI_TSDF_KERNEL_AUTO)
     ctx.set_option(_lib.DMI_OPT_CULL, args.cull)
+    quota = args.quota if args.quota > 0 else (32 if world == 1 else 8)
+    ctx.set_option(_lib.DMI_OPT_BRICK_QUOTA, quota)
     ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
     ctx.set_slab(k0, k1)
 
@@ -654,7 +657,7 @@ def main():
             "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H}, best-cost threshold {THRESH}, f64 volume",
                        "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views exchanged in groups of {G} ({EXCHANGE_TEXT[args.exchange]})" if world > 1 else ""),
                        "l2": "inputs (%.1f GB per step) exceed L2; no flush needed" % (algorithmic_bytes(N, V, W, H) / 1e9),
-                       "kernel": args.kernel, "cull": args.cull, "cost_model": args.cost_model},
+                       "kernel": args.kernel, "cull": args.cull, "cost_model": args.cost_model, "brick_quota": quota},
             "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
             "volume_digest": digest,
         }

@@ -26,6 +26,7 @@ DMI_OPT_TSDF_KERNEL = 1
 DMI_OPT_VIEW_CHUNK = 2
 DMI_OPT_TIER_COUNTERS = 3
 DMI_OPT_CULL = 4
+DMI_OPT_BRICK_QUOTA = 5
 
 
 class DmiError(RuntimeError):

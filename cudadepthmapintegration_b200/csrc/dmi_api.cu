@@ -84,6 +84,7 @@ struct dmi_ctx
   DevBuf counters, cls, tiles, viewscratch, maskscratch;
   bool counters_on = false;
   bool opt_cull = true;
+  int opt_quota = 32;
   std::string err;
 
   int fail(int code, const std::string& msg) { err = msg; return code; }
@@ -215,6 +216,9 @@ int dmi_set_option(dmi_ctx* ctx, int option, long long value)
       ctx->opt_kernel = value; return DMI_OK;
     case DMI_OPT_CULL:
       ctx->opt_cull = value != 0; return DMI_OK;
+    case DMI_OPT_BRICK_QUOTA:
+      DMI_REQUIRE(value >= 1 && value <= (1 << 20), "brick quota must be between 1 and 2^20");
+      ctx->opt_quota = (int)value; return DMI_OK;
     case DMI_OPT_TIER_COUNTERS:
       ctx->counters_on = value != 0;
       if (ctx->counters_on)
@@ -416,9 +420,9 @@ static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_dep
     DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths ? d_depths + npix * v0 : nullptr, d_lo ? d_lo + npix * v0 : nullptr, d_cls + npix * v0, clsSpare - (long long)(npix * (size_t)v0),
                                  d_tiles + tilesPerView * v0, ctx->opt_cull, (dmi::ViewFast*)ctx->viewscratch.p,
                                  (unsigned*)ctx->maskscratch.p, ctx->vol.p, ctx->vol_type,
-                                 ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr, ctx->stream));
+                                 ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr, ctx->opt_quota, ctx->stream));
     ctx->tsdf_stats.launches++;
-    ctx->total_launches += ctx->opt_cull ? 3 : 2;         // view staging, supertile culling, integration
+    ctx->total_launches += ctx->opt_cull ? 4 : 3;         // view staging, supertile culling, compaction, integration
   }
   return DMI_OK;
 }

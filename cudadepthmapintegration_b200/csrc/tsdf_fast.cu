@@ -653,14 +653,16 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
 // global counter until none is left (a launch over all bricks would spend ~2 ns on each of the many bricks
 // no view of the chunk can touch).  5 CTAs per SM (96 registers, ~130 bytes of spills in the rare tiers):
 // measured on config5, ms per step at 3 / 4 / 5 / 6 CTAs per SM = 292 / 254 / 238 / 246 -- the gathers'
-// latency wants warps more than the loop wants registers.
+// latency wants warps more than the loop wants registers.  A CTA retires after kBrickQuota bricks, so that
+// higher-priority kernels of other streams (the next views' preparation, NCCL) find a free slot within a
+// fraction of a millisecond instead of waiting for the whole launch (quota: DMI_OPT_BRICK_QUOTA).
 template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
 __global__ void __launch_bounds__(FT, 5)
 tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
                  const double* __restrict__ depths, const int* __restrict__ lo, const float* __restrict__ cls,
                  const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
                  long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
-                 const int* __restrict__ stlist, int* __restrict__ work,
+                 const int* __restrict__ stlist, int* __restrict__ work, int quota,
                  T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters)
 {
   static_assert(kFastChunk <= FT, "one pre-pass thread per view");
@@ -669,7 +671,7 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   __shared__ int s_item;
   constexpr int per = FSI * FSJ * FSK;
   const int nItems = work[0] * per;
-  for (;;)
+  for (int it = 0; it < quota; it++)
   {
     __syncthreads();                                          // the previous brick is done with shared memory
     if (threadIdx.x == 0) s_item = atomicAdd(work + 1, 1);
@@ -694,21 +696,22 @@ __global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant_
   if ((int)threadIdx.x < c.n) dst[threadIdx.x].pad[0] = tiles[(size_t)threadIdx.x * perView + flagOff];
 }
 
-// CTAs that are resident at once on this device for `kernel` (never more than there are bricks)
-static unsigned persistent_grid(const void* kernel, unsigned bricks)
+// Enough CTAs to take every brick at `quota` each, at least as many as are resident at once on this device
+static unsigned persistent_grid(const void* kernel, unsigned bricks, unsigned quota)
 {
   int dev = 0, sms = 0, perSm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, FT, 0);
-  return std::max(1u, std::min(bricks, (unsigned)(std::max(sms, 1) * std::max(perSm, 1))));
+  const unsigned resident = (unsigned)(std::max(sms, 1) * std::max(perSm, 1));
+  return std::max(1u, std::min(bricks, std::max(resident, (bricks + quota - 1) / quota)));
 }
 
 template <typename T, bool PINHOLE>
 static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                            const float* d_cls, const float* d_tileDmax, const TilePyramid& pyr, bool cull,
                            long long clsSpare, const ViewFast* d_views, unsigned* d_masks, T* d_vol, int nbi, int nbj,
-                           int nbk, FastCounters* d_counters, cudaStream_t s)
+                           int nbk, FastCounters* d_counters, int quota, cudaStream_t s)
 {
   const int nst = (int)(grid / (FSI * FSJ * FSK));
   if (cull)
@@ -718,8 +721,8 @@ static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& 
   int* work = list + nst;
   compact_supertiles_kernel<<<1, 1024, 0, s>>>(d_masks, nst, cull ? 1 : 0, list, work);
 #define DMI_LAUNCH_FAST(COUNT, SPLIT, CNT)                                                                         \
-  tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT><<<persistent_grid((const void*)tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT>, grid), FT, 0, s>>>( \
-      g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, list, work, d_vol, nbi, nbj, nbk, CNT)
+  tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT><<<persistent_grid((const void*)tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT>, grid, (unsigned)quota), FT, 0, s>>>( \
+      g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, list, work, quota, d_vol, nbi, nbj, nbk, CNT)
   if (d_counters) { if (d_depths) DMI_LAUNCH_FAST(true, false, d_counters); else DMI_LAUNCH_FAST(true, true, d_counters); }
   else { if (d_depths) DMI_LAUNCH_FAST(false, false, nullptr); else DMI_LAUNCH_FAST(false, true, nullptr); }
 #undef DMI_LAUNCH_FAST
@@ -735,8 +738,9 @@ size_t tsdf_fast_mask_bytes(const GridParams& g)
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
                              ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
-                             FastCounters* d_counters, cudaStream_t s)
+                             FastCounters* d_counters, int quota, cudaStream_t s)
 {
+  quota = std::max(1, quota);
   const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
   if (nbi <= 0 || nbj <= 0 || nbk <= 0 || c.n <= 0) return cudaSuccess;
   const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
@@ -747,13 +751,13 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
   const ViewFast* d_views = d_viewScratch;
   if (scalarType == 1)
   {
-    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
-    else launch_variant<double, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, s);
+    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
+    else launch_variant<double, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
   }
   else
   {
-    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
-    else launch_variant<float, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, s);
+    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
+    else launch_variant<float, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
   }
   return cudaGetLastError();
 }

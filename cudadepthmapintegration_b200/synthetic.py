@@ -145,7 +145,9 @@ def render_views(K: np.ndarray, RT: np.ndarray, width: int, height: int, *, seed
     dy = ((py - cy) / fy).expand(n, H, W)
     R = RTt[:, :3, :3]
     t = RTt[:, :3, 3]
-    C = -torch.einsum("nij,ni->nj", R, t)                     # camera centre, world
+    # camera centre, world: -R^T t, spelled out element by element so that a view's maps do not depend on how
+    # many views are rendered in one call (a batched matmul may pick another kernel, and rounding, for n == 1)
+    C = -(R[:, 0, :] * t[:, 0:1] + R[:, 1, :] * t[:, 1:2] + R[:, 2, :] * t[:, 2:3])
     # world direction = R^T (dx, dy, 1)
     dw = [R[:, 0, a].view(n, 1, 1) * dx + R[:, 1, a].view(n, 1, 1) * dy + R[:, 2, a].view(n, 1, 1) for a in range(3)]
     a = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]

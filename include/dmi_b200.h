@@ -62,6 +62,8 @@ extern "C" {
 #define DMI_OPT_VIEW_CHUNK 2         /* views per launch (0 = auto) */
 #define DMI_OPT_TIER_COUNTERS 3      /* 1: count tier decisions of the fast kernel (diagnostic build of the kernel) */
 #define DMI_OPT_CULL 4               /* 1 (default): skip (brick, view) pairs that provably contribute nothing */
+#define DMI_OPT_BRICK_QUOTA 5        /* bricks a CTA of the integration kernel takes before it retires (default 32);
+                                        lower it when higher-priority work on other streams must get in quickly */
 
 typedef struct dmi_ctx dmi_ctx;
 
