@@ -262,6 +262,8 @@ def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+# (workload, kernel, n_gpus) -> DRAM bytes per launch measured by ncu (mean of the two captured launches)
+NCU_DRAM_BYTES_PER_LAUNCH = {("config5", "auto", 1): 8.86e9}
 EXCHANGE_TEXT = {"fused": "prepared by their owner straight into every rank's buffers: stores over NVLink from the preparation kernel",
                  "ce": "copy-engine pushes over CUDA IPC", "nccl": "NCCL all-gather"}
 _JSON_OUT = None
@@ -627,7 +629,10 @@ def main():
         alg_bytes = algorithmic_bytes(N, V, W, H) / world * args.steps
         roofline = {
             "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the integration kernel, from the committed
+            # ncu --set full capture of this workload (profiles/r1_tsdf_fast_config5_ncu_full.txt); config5 only
+            "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, args.kernel, world)),
+            "traffic_unit": "bytes per launch (algorithmic: %.3g)" % (alg_bytes / max(kernel_launches, 1)),
             "kernel": "tsdf_fast_kernel" if args.kernel != "exact" else "tsdf_exact_kernel",
             "definition": "28 algorithmic flops x the voxel*view pairs the kernel EVALUATED one by one (pairs settled by the exact "
                           "brick tests -- culled, or free space in front of the surface: one add -- are excluded) / summed CUDA-event time of the integration launches of the timed region",
