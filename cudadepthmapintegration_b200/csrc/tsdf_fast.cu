@@ -8,22 +8,28 @@
 // bit-for-bit; only the continuous values (camera z, the linear branch) differ from the reference's
 // rounding by a few ulp of double.  Error bounds are derived in DESIGN.md ("certification").
 //
-// Per CTA: a brick of 16 x 8 x 8 voxels (4 warps of 8 x 4 lanes, 8 voxels per thread along k) and a
-// chunk of up to 64 views.
-//   pre-pass   one thread per view: FP64 brick base of the projective rows -> float; projected bounding
-//              box of the brick; CULL the view when every voxel is behind the camera, outside the image,
+// Work item: a brick of 16 x 8 x 8 voxels (4 warps of 8 x 4 lanes, 8 voxels per thread along k) against a chunk of
+// up to 64 views.  A persistent grid (5 CTAs per SM) takes the bricks of the supertiles (64 x 32 x 32 voxels) that
+// some view of the chunk may touch from a global counter.
+//   supertile  one thread per (supertile, view): the exact box tests below on the supertile's box -> 64-bit view
+//              masks, compacted into the list of active supertiles
+//   pre-pass   one thread per view the supertile kept: FP64 brick base of the projective rows -> float; projected
+//              bounding box of the brick; CULL the view when every voxel is behind the camera, outside the image,
 //              over tiles without a valid pixel, or farther than Delta behind every valid depth of its
-//              footprint (all of which contribute exactly nothing); per-brick error scales; survivors
-//              are compacted in view order into shared memory.
+//              footprint (all of which contribute exactly nothing); FREE SPACE when every voxel lands on fully
+//              valid tiles farther than Delta in front of every depth there (the view adds -Eta*Rho to every
+//              voxel: one add each); per-brick error scales; survivors are compacted in view order into shared
+//              memory.  Footprint statistics come from per-view sparse tables (4 loads, see dmi_internal.cuh).
 //   phase A    T1, FP32: 3 FFMA + MUFU.RCP + 2 FFMA give the centred pixel rounded by the magic-number
 //              add; 2 more FFMA its distance to the integer; certified when that distance is below
-//              0.5 - (E*r + c0).  Uncertified voxels (~0.1 %) go to
+//              0.5 - (E*r + c0).  Uncertified voxels (~0.06 %) go to
 //              T2, FP64: composed rows (9 DFMA) + residual test of the candidate and its neighbours, and
 //              T3, the reference's own operation sequence, when T2 meets a tie within 2^-44.
 //   phase B    gather of the FLOAT classification image (4 B per voxel*view)
 //   phase C    FP32: invalid / farther than Delta (certified with margin) -> add 0 or -Eta*Rho; the thin
-//              band around the surface re-gathers the double depth and evaluates the potential in FP64
-//              (T3 when |diff| is within 2^-44 of Delta, the potential's only discontinuity).
+//              band around the surface re-gathers the double depth (or rebuilds it from the classification
+//              float and the int32 residual image) and evaluates the potential in FP64 (T3 when |diff| is within
+//              2^-44 of Delta, the potential's only discontinuity).
 // Views are accumulated in list order per voxel, like the reference's host loop (:343).
 #include "dmi_internal.cuh"
 #include "tsdf_device.cuh"

@@ -59,3 +59,38 @@ def test_render_is_device_independent_in_its_random_fields():
     _, b2, c2 = syn.render_views(K[1:], RT[1:], 32, 24, first_view=1)
     assert np.array_equal(b1.numpy()[1:], b2.numpy())                 # hash depends on the global view index
     assert np.array_equal(c1.numpy()[1:], c2.numpy())
+
+
+@pytest.mark.parametrize("V,G,world", [(1000, 128, 8), (1000, 128, 2), (100, 16, 4), (7, 4, 1), (10, 128, 2), (64, 64, 8)])
+def test_view_groups_cover_all_views_in_order_with_short_ends(V, G, world):
+    """Groups are consecutive, cover [0, V) once, every size but the last is a multiple of the world size, and
+    with more than one rank both ends are shorter than a full group (integration starts early, the tail is short)."""
+    from cudadepthmapintegration_b200 import distributed as D
+    groups = D.view_groups(V, G, world)
+    assert groups[0][0] == 0 and groups[-1][1] == V
+    for (a0, a1), (b0, b1) in zip(groups, groups[1:]):
+        assert a1 == b0 and a1 > a0
+    assert all((b - a) % world == 0 for a, b in groups[:-1])
+    full = max(world, G // world * world)
+    assert all(b - a <= full for a, b in groups)
+    if world > 1 and V >= 4 * full:
+        assert groups[0][1] - groups[0][0] < full and groups[-1][1] - groups[-1][0] < full
+    # every view has exactly one owner, and owners hold their views in increasing order
+    owners = [v for r in range(world) for v in D.owned_views(V, G, r, world)]
+    assert sorted(owners) == list(range(V))
+    for r in range(world):
+        mine = D.owned_views(V, G, r, world)
+        assert list(mine) == sorted(mine)
+
+
+def test_render_views_do_not_depend_on_the_batch():
+    """A view's synthetic maps are the same whether it is rendered alone or in a batch (multi-GPU ranks render the
+    runs of views they own; a batch-dependent rounding would make their volumes differ from the single-GPU one)."""
+    import numpy as np
+    from cudadepthmapintegration_b200 import synthetic as syn
+    K, RT = syn.make_cameras(9, 96, 72)
+    d, c, col = syn.render_views(K, RT, 96, 72, depth_noise=0.01)
+    for i in (0, 4, 8):
+        d1, c1, col1 = syn.render_views(K[i:i + 1], RT[i:i + 1], 96, 72, first_view=i, depth_noise=0.01)
+        assert np.array_equal(d1[0].numpy(), d[i].numpy()) and np.array_equal(c1[0].numpy(), c[i].numpy())
+        assert np.array_equal(col1[0].numpy(), col[i].numpy())
