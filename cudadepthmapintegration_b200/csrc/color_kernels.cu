@@ -116,7 +116,7 @@ __device__ __forceinline__ int select_rank(const unsigned c[8], unsigned before,
 // Histograms: 3 channels x 256 bins x 16-bit counters per point, two bins per 32-bit word (shared-memory
 // atomics are 32-bit); requires nViews < 65536, which the launcher checks.
 template <typename XYZ, int Q>
-__global__ void __launch_bounds__(32 * kColorWarps, 3)
+__global__ void __launch_bounds__(32 * kColorWarps, 2)
 colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_constant__ ColorViews views,
                 const uint8_t* __restrict__ colors, int W, int H,
                 uint8_t* __restrict__ mean, uint8_t* __restrict__ median, int32_t* __restrict__ nb)
