@@ -305,9 +305,18 @@ static bool host_bytes_all_zero(const void* p, size_t bytes)
   if (nt == 1) scan(0, words);
   else
   {
+    // no exception may cross the C ABI: a thread that cannot be created leaves its share to the caller's thread
     std::vector<std::thread> th;
     const size_t per = (words + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; t++) th.emplace_back(scan, std::min(words, t * per), std::min(words, (t + 1) * per));
+    unsigned started = 0;
+    try
+    {
+      th.reserve(nt);
+      for (; started < nt; started++)
+        th.emplace_back(scan, std::min(words, started * per), std::min(words, (started + 1) * per));
+    }
+    catch (...) {}
+    for (unsigned t = started; t < nt; t++) scan(std::min(words, t * per), std::min(words, (t + 1) * per));
     for (auto& t : th) t.join();
   }
   return !nonzero.load();
@@ -645,10 +654,14 @@ int dmi_process_depth_maps(dmi_ctx* ctx, int nViews, const double* depths, const
   // verified by a full host scan WHILE the views stream in and integrate onto a zeroed device volume; should
   // the scan find a set bit after all, the pass is repeated from the uploaded io_scalar (inputs are still here).
   const size_t bytes = slab_cells(ctx->g) * (scalarType == DMI_F64 ? 8 : 4);
-  const bool speculate = bytes >= (256u << 20) && host_zero_probe(io_scalar, bytes);
+  bool speculate = bytes >= (256u << 20) && host_zero_probe(io_scalar, bytes);
   bool zero = true;
   std::thread scan;
-  if (speculate) scan = std::thread([&] { zero = host_bytes_all_zero(io_scalar, bytes); });
+  if (speculate)
+  {
+    try { scan = std::thread([&] { zero = host_bytes_all_zero(io_scalar, bytes); }); }
+    catch (...) { speculate = false; }               // no thread: scan synchronously inside volume_begin
+  }
   int rc = volume_begin_impl(ctx, io_scalar, scalarType, speculate ? kVolAssumeZero : kVolScan);
   if (rc == DMI_OK) rc = dmi_volume_integrate_host(ctx, nViews, depths, bestCost, thresholdBestCost, K, RT);
   if (speculate) scan.join();
