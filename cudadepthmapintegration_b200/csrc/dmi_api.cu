@@ -39,14 +39,24 @@ struct KernelStats
   std::vector<EventSpan> pending;
   std::vector<EventSpan> pool;
   long long launches = 0;
+  float carry = 0.f;                   // time of spans recycled before anybody asked for the statistics
   EventSpan open() {
     EventSpan s;
+    if (pending.size() >= 1024)        // a caller that never reads the statistics must not accumulate events
+    {
+      s = pending.front();
+      pending.erase(pending.begin());
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) carry += ms; else cudaGetLastError();
+      return s;
+    }
     if (!pool.empty()) { s = pool.back(); pool.pop_back(); }
     else { cudaEventCreate(&s.a); cudaEventCreate(&s.b); }
     return s;
   }
   float drain() {
-    float total = 0.f;
+    float total = carry;
+    carry = 0.f;
     for (auto& s : pending) { float ms = 0.f; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) total += ms; pool.push_back(s); }
     pending.clear();
     return total;
@@ -456,7 +466,7 @@ static int integrate_fast_resident(dmi_ctx* ctx, int nViews, const double* d_dep
     const int gn = std::min(group, nViews - g0);
     DMI_CK(dmi::launch_prepare_views(d_depths + npix * g0, d_cost ? d_cost + npix * g0 : nullptr, thr, gn, g.W, g.H,
                                      (float*)ctx->cls.p, nullptr, (long long)(npix * (size_t)gn), (float*)ctx->tiles.p, ctx->stream));
-    ctx->total_launches++;
+    ctx->total_launches += 1 + dmi::tile_pyramid_layout(ctx->g.W, ctx->g.H).nLevels;   // level 0, upper levels, flag
     int rc = integrate_fast_prepared(ctx, gn, d_depths + npix * g0, nullptr, (const float*)ctx->cls.p, (long long)(npix * (size_t)gn),
                                      (const float*)ctx->tiles.p, K + 16 * (size_t)g0, RT + 16 * (size_t)g0);
     if (rc != DMI_OK) return rc;
@@ -535,7 +545,7 @@ int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, c
   DMI_CK(cudaSetDevice(ctx->device));
   DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, d_cls, d_lo, clsSpareIndex,
                                    d_tileStats, ctx->stream));
-  ctx->total_launches++;
+  ctx->total_launches += 1 + dmi::tile_pyramid_layout(ctx->g.W, ctx->g.H).nLevels;   // level 0, upper levels, flag
   return DMI_OK;
 }
 
@@ -560,7 +570,7 @@ int dmi_prepare_views_multi(dmi_ctx* ctx, int nViews, const double* d_depths, co
   dst.aligned = (bits & 31) == 0;
   DMI_CK(cudaSetDevice(ctx->device));
   DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, dst, clsSpareIndex, ctx->stream));
-  ctx->total_launches++;
+  ctx->total_launches += 1 + dmi::tile_pyramid_layout(ctx->g.W, ctx->g.H).nLevels;   // level 0, upper levels, flag
   return DMI_OK;
 }
 
