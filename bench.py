@@ -654,6 +654,7 @@ def main():
                                  "exact_tier": tiers["t3_entered"] / u, "band_fp64": tiers["near_band"] / u,
                                  "far_front": tiers["far_front"] / u, "far_behind": tiers["far_behind"] / u,
                                  "invalid_or_rejected": tiers["invalid_or_rejected"] / u,
+                                 "validity_only_phase_c": tiers["validity_only"] / u,
                                  "note": "fractions of the evaluated pairs (rank 0)"}
         line = {
             "metric": "voxel*view updates/sec", "value": value, "unit": "voxel*views/s", "n_gpus": world,

@@ -72,26 +72,28 @@ struct FastCounters               // optional diagnostics (device memory, may be
 {
   unsigned long long t1_certified, t2_entered, t3_entered, delta_guard, units, culled, near_band, brick_views;
   unsigned long long uniform_front;     // voxel*views settled brick-wide by one add per voxel, see eval_box
-  unsigned long long reserved[7];       // [0] far in front, [1] far behind, [2] invalid pixel (voxel*views, FP32 phase C)
+  unsigned long long reserved[7];       // [0] far in front, [1] far behind, [2] invalid pixel (voxel*views, FP32 phase C),
+                                        // [3] of [0]+[2]: settled by the validity-only phase C
 };
 
 // Per-view data the fast kernel gathers from, built by launch_prepare_views:
 //   cls       float[n][H][W]   depth rounded to float, -1.0f exactly on the pixels that are invalid after
 //                              the best-cost filter (never -1.0f on a valid pixel)
-//   tileStats float[n][perView] per 8x8 tile of storage rows: max valid depth (rounded up), -inf when the
-//                              tile has no valid pixel, +inf when it holds a NaN; and, minOff floats further,
-//                              min depth (rounded down) when EVERY pixel of the tile inside the image is valid
-//                              and not NaN, -inf otherwise
-// The statistics form a sparse table per view: level l holds, AT EVERY TILE POSITION (x, y), the statistic
-// of the window of 2^l x 2^l tiles whose corner is (x, y) (clipped by the image).  Any rectangle of tiles is
+//   tileStats float[n][perView] per 8x8 tile of storage rows, as {max, min} pairs (float2): max of the valid depths
+//                              (rounded up; -inf when the tile has no valid pixel, +inf when it holds a NaN) and
+//                              min of the valid depths (rounded down; +inf when none, -inf with a NaN); and,
+//                              badOff floats from the view's start, 1.0f when the tile holds an invalid pixel or a
+//                              NaN (inside the image), else 0.0f
+// The statistics form sparse tables per view: level l holds, AT EVERY TILE POSITION (x, y), the statistic of
+// the window of 2^l x 2^l tiles whose corner is (x, y) (clipped by the image).  Any rectangle of tiles is
 // the union of four overlapping windows of level floor(log2(longer side)): exact along the longer side,
 // at most 2x over-covered along the shorter one -- tight bounds for a brick footprint of any size in 4 loads.
 struct TilePyramid
 {
   int nLevels;
   int tw, th;                     // tiles per row / column; every level has tw * th entries
-  int perView;                    // floats per view: both tables + the flag
-  int minOff;                     // the min table starts here; level l of either table at l * tw * th
+  int perView;                    // floats per view: the {max, min} table, the bad table, the flag; multiple of 4
+  int badOff;                     // the bad table starts here; level l of either table at l * tw * th entries
   int flagOff;                    // one float: 1.0f when some tile of the view is fully valid
 };
 TilePyramid tile_pyramid_layout(int W, int H);

@@ -102,6 +102,32 @@ __device__ __forceinline__ void classify_far(float& acc, unsigned& near, float n
       "}" : "+f"(acc), "+r"(near) : "f"(ner), "f"(fc), "f"(d32), "f"(thr), "r"(bit));
 }
 
+// Phase C of a view for which the whole brick is certainly farther than Delta in front of every valid depth it can
+// meet: acc += ner when the gathered pixel is valid (anything but -1.0f), else nothing.
+__device__ __forceinline__ void add_if_valid(double& acc, double ner, float d32)
+{
+  asm("{\n\t"
+      ".reg .pred pv;\n\t"
+      ".reg .b32 shi, zero;\n\t"
+      ".reg .f64 sel;\n\t"
+      "mov.b32 zero, 0;\n\t"
+      "setp.neu.f32 pv, %2, 0fBF800000;\n\t"
+      "selp.b32 shi, 0x3FF00000, 0, pv;\n\t"
+      "mov.b64 sel, {zero, shi};\n\t"
+      "fma.rn.f64 %0, %1, sel, %0;\n\t"
+      "}" : "+d"(acc) : "d"(ner), "f"(d32));
+}
+__device__ __forceinline__ void add_if_valid(float& acc, float ner, float d32)
+{
+  asm("{\n\t"
+      ".reg .pred pv;\n\t"
+      ".reg .f32 sel;\n\t"
+      "setp.neu.f32 pv, %2, 0fBF800000;\n\t"
+      "selp.f32 sel, 0f3F800000, 0f00000000, pv;\n\t"
+      "fma.rn.f32 %0, %1, sel, %0;\n\t"
+      "}" : "+f"(acc) : "f"(ner), "f"(d32));
+}
+
 __device__ __forceinline__ double affine(const double* r, double di, double dj, double dk)
 {
   return fma(di, r[0], fma(dj, r[1], fma(dk, r[2], r[3])));
@@ -201,30 +227,46 @@ __device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c,
   return true;
 }
 
-// Max (or all-valid min) of the depths over a pixel rectangle (storage coordinates) from the view's sparse
-// table: four overlapping windows of 2^l x 2^l tiles, l = floor(log2(longer side in tiles)); all four loads
-// are in flight together.
-template <bool MIN>
-__device__ __forceinline__ float footprint_stat(const TilePyramid& pyr, const float* __restrict__ td, const BrickBox& b)
+// Statistics of the depths over a pixel rectangle (storage coordinates) from the view's sparse tables: four
+// overlapping windows of 2^l x 2^l tiles, l = floor(log2(longer side in tiles)); the four loads of a table are
+// in flight together.  {max, min} of the valid depths come in one 8-byte entry.
+struct FootIdx { int o00, o01, o10, o11; };
+__device__ __forceinline__ FootIdx footprint_index(const TilePyramid& pyr, const BrickBox& b)
 {
   const int X0 = b.tx0 >> 3, X1 = min(b.tx1 >> 3, pyr.tw - 1), Y0 = b.ty0 >> 3, Y1 = min(b.ty1 >> 3, pyr.th - 1);
   const int n = max(X1 - X0, Y1 - Y0) + 1;
   const int l = min(31 - __clz(n), pyr.nLevels - 1);          // nLevels covers every n <= max(tw, th)
   const int sdim = 1 << l;
   const int xb = max(X0, X1 - sdim + 1), yb = max(Y0, Y1 - sdim + 1);
-  const float* t = td + (size_t)l * (pyr.tw * pyr.th) + (MIN ? pyr.minOff : 0);
-  const float a = __ldg(t + Y0 * pyr.tw + X0), bq = __ldg(t + Y0 * pyr.tw + xb);
-  const float cq = __ldg(t + yb * pyr.tw + X0), dq = __ldg(t + yb * pyr.tw + xb);
-  return MIN ? fminf(fminf(a, bq), fminf(cq, dq)) : fmaxf(fmaxf(a, bq), fmaxf(cq, dq));
+  const int base = l * (pyr.tw * pyr.th);
+  FootIdx ix;
+  ix.o00 = base + Y0 * pyr.tw + X0; ix.o01 = base + Y0 * pyr.tw + xb;
+  ix.o10 = base + yb * pyr.tw + X0; ix.o11 = base + yb * pyr.tw + xb;
+  return ix;
+}
+// x = max of the valid depths (-inf: none, +inf: a NaN), y = min of the valid depths (+inf: none, -inf: a NaN)
+__device__ __forceinline__ float2 footprint_minmax(const float* __restrict__ td, const FootIdx& ix)
+{
+  const float2* t = reinterpret_cast<const float2*>(td);
+  const float2 a = __ldg(t + ix.o00), b = __ldg(t + ix.o01), c = __ldg(t + ix.o10), d = __ldg(t + ix.o11);
+  return make_float2(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fminf(fminf(a.y, b.y), fminf(c.y, d.y)));
+}
+// 0 when every pixel of the rectangle's windows is valid and not NaN
+__device__ __forceinline__ float footprint_bad(const TilePyramid& pyr, const float* __restrict__ td, const FootIdx& ix)
+{
+  const float* t = td + pyr.badOff;
+  return fmaxf(fmaxf(__ldg(t + ix.o00), __ldg(t + ix.o01)), fmaxf(__ldg(t + ix.o10), __ldg(t + ix.o11)));
 }
 
 // Everything the pre-pass needs to know about (box of voxels, view): FP64 base of the rows at the box
 // origin rounded to float, |u| bounds over the box, and whether the view can be CULLED for the whole box:
 // every voxel behind the camera (:177), outside the image (:192-197), over tiles without a valid pixel
 // (:202), or farther than Delta BEHIND every valid depth it can meet (rayPotential returns 0, :114-115).
-// `front`: every voxel of the box lands inside the image on a valid pixel and is farther than Delta IN FRONT
-// of every depth it can meet: the view adds exactly -Eta*Rho to every voxel (:114-115), no projection needed.
-struct BoxEval { bool keep, front; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs; };
+// `front` = 2: the whole box lies farther than Delta IN FRONT of every valid depth it can meet: a voxel's
+// contribution is -Eta*Rho when its pixel is valid and nothing otherwise (:114-115, :202), so phase C only
+// looks at validity.  `front` = 1: moreover every voxel lands inside the image on a valid pixel:
+// the view adds exactly -Eta*Rho to every voxel, no projection needed.
+struct BoxEval { bool keep; int front; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs; };
 
 template <bool PINHOLE>
 __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& c, const TilePyramid& pyr,
@@ -253,7 +295,7 @@ __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& 
   }
   o.czmaxabs = fmaxf(fabsf(clo), fabsf(chi));
   o.keep = true;
-  o.front = false;
+  o.front = 0;
   BrickBox box; box.valid = false; box.inside = false;
   bool outside = false;
   const bool boxed = brick_box(V, c, o.fbx, o.fby, o.fbz, ei, ej, ek, lx, ly, lz, zlo, W, H, box, outside);
@@ -264,10 +306,12 @@ __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& 
     else if (boxed && outside) o.keep = false;
     else if (boxed && box.valid)
     {
-      const float dmax = footprint_stat<false>(pyr, td, box);
+      const FootIdx ix = footprint_index(pyr, box);
+      const float2 mm = footprint_minmax(td, ix);
       const float thr = c.delta_up + 1e-6f * o.czmaxabs;
-      if (dmax == -INFINITY || clo - dmax > thr) o.keep = false;
-      else if (box.inside && V.pad[0] != 0.f && footprint_stat<true>(pyr, td, box) - chi > thr) o.front = true;
+      if (mm.x == -INFINITY || clo - mm.x > thr) o.keep = false;
+      else if (mm.y - chi > thr)                               // a NaN in the footprint makes mm.y -inf
+        o.front = (box.inside && V.pad[0] != 0.f && footprint_bad(pyr, td, ix) == 0.f) ? 1 : 2;
     }
   }
   return o;
@@ -382,7 +426,7 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
       int pos = __popc(bal & ((1u << lane) - 1u));
       for (int q = 0; q < w; q++) pos += s_cnt[q];
       ViewSm& S = s_view[pos];
-      S.pad = e.front ? 1 : 0;
+      S.pad = e.front;
       const float Ex = c.k3 * ((fabsf(e.fbx) + 3.f * V.lx) + e.Ux * (fabsf(e.fbz) + 3.f * V.lz));
       const float Ey = c.k3 * ((fabsf(e.fby) + 3.f * V.ly) + e.Uy * (fabsf(e.fbz) + 3.f * V.lz));
       S.base = make_float4(e.fbx, e.fby, e.fbz, V.zm);
@@ -434,12 +478,12 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
   const int negW = -W;
   const double delta = g.delta, thick = g.thick;
   const T nerT = (T)g.neg_eta_rho;
-  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0, n_uf = 0, n_front = 0, n_behind = 0, n_inv = 0;
+  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0, n_uf = 0, n_front = 0, n_behind = 0, n_inv = 0, n_light = 0;
 
   for (int q = 0; q < nsurv; q++)
   {
     const ViewSm& S = s_view[q];
-    if (S.pad)                                                // CTA-uniform: the whole brick is free space for this view
+    if (S.pad == 1)                                           // CTA-uniform: the whole brick is free space for this view
     {
 #pragma unroll
       for (int m = 0; m < FM; m++) acc[m] = add_rn(acc[m], nerT);
@@ -550,6 +594,17 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
     }
     if (!anyh[0] && !anyh[1]) continue;
 
+    if (S.pad == 2)                                            // CTA-uniform: only validity matters for this view
+    {
+#pragma unroll
+      for (int m = 0; m < FM; m++)
+      {
+        add_if_valid(acc[m], nerT, d32[m]);
+        if (COUNT) { if (d32[m] == -1.0f) n_inv++; else { n_front++; n_light++; } }
+      }
+      continue;
+    }
+
     // ---- phase C: FP32 classification; -1.0f = invalid after the filter (:202).  In front and farther
     // than Delta (certified by the margin in thrfar): -Eta*Rho; behind and farther: 0 (:114-115);
     // everything else that is valid (NaN included) goes to the FP64 band below.
@@ -626,10 +681,10 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
   {
     // one atomic per warp and counter (the lanes that returned early above are simply absent)
     const unsigned act = __activemask();
-    unsigned long long vals[10] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)nk * (nsurv - n_uf), n_front, n_behind, n_inv,
-                                   (unsigned long long)nk * n_uf};
+    unsigned long long vals[11] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)nk * (nsurv - n_uf), n_front, n_behind, n_inv,
+                                   (unsigned long long)nk * n_uf, n_light};
 #pragma unroll
-    for (int q = 0; q < 10; q++)
+    for (int q = 0; q < 11; q++)
     {
       unsigned long long x = vals[q];
       for (int o = 16; o > 0; o >>= 1)
@@ -651,6 +706,7 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
       atomicAdd(&counters->reserved[1], vals[7]);
       atomicAdd(&counters->reserved[2], vals[8]);
       atomicAdd(&counters->uniform_front, vals[9]);
+      atomicAdd(&counters->reserved[3], vals[10]);
     }
   }
 }
@@ -780,9 +836,10 @@ TilePyramid tile_pyramid_layout(int W, int H)
   int m = std::max(std::max(p.tw, p.th), 1), l = 0;
   while ((2 << l) <= m) l++;                                  // floor(log2(m))
   p.nLevels = l + 1;
-  p.minOff = p.nLevels * p.tw * p.th;
-  p.flagOff = 2 * p.minOff;
-  p.perView = p.flagOff + 4;
+  const int L = p.nLevels * p.tw * p.th;
+  p.badOff = 2 * L;
+  p.flagOff = 3 * L;
+  p.perView = (p.flagOff + 4 + 3) / 4 * 4;                    // every view's statistics start 16-byte aligned
   return p;
 }
 
@@ -791,7 +848,7 @@ TilePyramid tile_pyramid_layout(int W, int H)
 // its all-gather.
 __global__ void __launch_bounds__(256)
 prepare_views_kernel(const double* __restrict__ depths, const double* __restrict__ cost, double thr,
-                     int nViews, int W, int H, int TW, int TH, int perView, int minOff,
+                     int nViews, int W, int H, int TW, int TH, int perView, int badOff,
                      const __grid_constant__ PrepareDst dst, long long clsSpare)
 {
   if (blockIdx.x == 0 && threadIdx.x == 0 && clsSpare >= 0)
@@ -805,7 +862,7 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
   const int t = (int)(blk % blocksPerView);
   const int by = t / BW, bx = t % BW;
   const int row = by * 16 + (lane >> 1), col = bx * 16 + (lane & 1) * 8;
-  float dmax = -INFINITY, dmin = INFINITY;
+  float dmax = -INFINITY, dmin = INFINITY, bad = 0.f;
   if (row < H && col < W)
   {
     const size_t base = (size_t)v * W * H + (size_t)row * W + col;
@@ -828,14 +885,15 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
           float up = f;
           if ((double)up < d) up = __int_as_float(__float_as_int(up) + (up >= 0.f ? 1 : -1));
           dmax = (d != d) ? INFINITY : fmaxf(dmax, up);
-          // tile minimum, rounded down; NaN or an invalid pixel poisons it (-inf: never "free space")
+          // tile minimum of the valid depths, rounded down; NaN poisons it (-inf: never "in front of everything")
           float dn = f;
           if ((double)dn > d) dn = __int_as_float(__float_as_int(dn) + (dn > 0.f ? -1 : 1));
           dmin = (d != d) ? -INFINITY : fminf(dmin, dn);
+          if (d != d) bad = 1.f;
           f8[q] = f;
           if (wantLo) l8[q] = split_encode(d, f);
         }
-        else dmin = -INFINITY;
+        else bad = 1.f;                                        // an invalid pixel: the tile is not fully valid
       }
     }
     const bool vec = ((W & 7) == 0) && dst.aligned;            // whole 32-byte groups, 32-byte aligned rows
@@ -867,19 +925,25 @@ prepare_views_kernel(const double* __restrict__ depths, const double* __restrict
   {
     dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
     dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    bad = fmaxf(bad, __shfl_xor_sync(0xffffffffu, bad, o));
   }
   const int tx = bx * 2 + (lane & 1), ty = by * 2 + (lane >> 4);
   if ((lane & 14) == 0 && tx < TW && ty < TH)
   {
-    const size_t o = (size_t)v * perView + ty * TW + tx;
-    for (int r = 0; r < dst.n; r++) { dst.tiles[r][o] = dmax; dst.tiles[r][o + minOff] = dmin; }
+    const size_t o = (size_t)v * perView;
+    const int q = ty * TW + tx;
+    for (int r = 0; r < dst.n; r++)
+    {
+      reinterpret_cast<float2*>(dst.tiles[r] + o)[q] = make_float2(dmax, dmin);
+      dst.tiles[r][o + badOff + q] = bad;
+    }
   }
 }
 
 // level l from level l-1: windows of 2^l tiles = four windows of 2^(l-1) tiles, h = 2^(l-1) apart (clipped);
 // read from the local copy, written everywhere
 __global__ void __launch_bounds__(256)
-tile_level_kernel(const __grid_constant__ PrepareDst dst, int nViews, int perView, int minOff, int tw, int th, int l)
+tile_level_kernel(const __grid_constant__ PrepareDst dst, int nViews, int perView, int badOff, int tw, int th, int l)
 {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t per = (size_t)tw * th;
@@ -887,20 +951,26 @@ tile_level_kernel(const __grid_constant__ PrepareDst dst, int nViews, int perVie
   const int v = (int)(t / per), q = (int)(t % per);
   const int y = q / tw, x = q % tw, h = 1 << (l - 1);
   const int x1 = min(x + h, tw - 1), y1 = min(y + h, th - 1);
-  const float* src = dst.tiles[0] + (size_t)v * perView + (size_t)(l - 1) * per;
-  const float mx = fmaxf(fmaxf(src[y * tw + x], src[y * tw + x1]), fmaxf(src[y1 * tw + x], src[y1 * tw + x1]));
-  const float* srn = src + minOff;
-  const float mn = fminf(fminf(srn[y * tw + x], srn[y * tw + x1]), fminf(srn[y1 * tw + x], srn[y1 * tw + x1]));
-  const size_t o = (size_t)v * perView + (size_t)l * per + q;
-  for (int r = 0; r < dst.n; r++) { dst.tiles[r][o] = mx; dst.tiles[r][o + minOff] = mn; }
+  const float* view = dst.tiles[0] + (size_t)v * perView;
+  const float2* src = reinterpret_cast<const float2*>(view) + (size_t)(l - 1) * per;
+  const float2 a = src[y * tw + x], b = src[y * tw + x1], c = src[y1 * tw + x], d = src[y1 * tw + x1];
+  const float2 mm = make_float2(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fminf(fminf(a.y, b.y), fminf(c.y, d.y)));
+  const float* srb = view + badOff + (size_t)(l - 1) * per;
+  const float bad = fmaxf(fmaxf(srb[y * tw + x], srb[y * tw + x1]), fmaxf(srb[y1 * tw + x], srb[y1 * tw + x1]));
+  const size_t o = (size_t)v * perView;
+  for (int r = 0; r < dst.n; r++)
+  {
+    reinterpret_cast<float2*>(dst.tiles[r] + o)[(size_t)l * per + q] = mm;
+    dst.tiles[r][o + badOff + (size_t)l * per + q] = bad;
+  }
 }
 
-// flag = 1.0f when some tile of the view is fully valid (its min statistic is finite or +inf)
-__global__ void __launch_bounds__(256) view_flag_kernel(const __grid_constant__ PrepareDst dst, int perView, int minOff, int flagOff, int n0)
+// flag = 1.0f when some tile of the view is fully valid
+__global__ void __launch_bounds__(256) view_flag_kernel(const __grid_constant__ PrepareDst dst, int perView, int badOff, int flagOff, int n0)
 {
-  const float* t = dst.tiles[0] + (size_t)blockIdx.x * perView + minOff;
+  const float* t = dst.tiles[0] + (size_t)blockIdx.x * perView + badOff;
   int any = 0;
-  for (int q = threadIdx.x; q < n0; q += blockDim.x) any |= (t[q] > -INFINITY) ? 1 : 0;
+  for (int q = threadIdx.x; q < n0; q += blockDim.x) any |= (t[q] == 0.f) ? 1 : 0;
   any = __syncthreads_or(any);
   if (threadIdx.x == 0)
     for (int r = 0; r < dst.n; r++) dst.tiles[r][(size_t)blockIdx.x * perView + flagOff] = any ? 1.0f : 0.0f;
@@ -913,11 +983,11 @@ cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, d
   const size_t blocks2x2 = (size_t)((p.tw + 1) / 2) * ((p.th + 1) / 2) * nViews;
   if (blocks2x2 == 0 || dst.n <= 0) return cudaSuccess;
   prepare_views_kernel<<<(unsigned)((blocks2x2 + 7) / 8), 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw, p.th, p.perView,
-                                                                       p.minOff, dst, clsSpare);
+                                                                       p.badOff, dst, clsSpare);
   const size_t n = (size_t)p.tw * p.th * nViews;
   for (int l = 1; l < p.nLevels; l++)
-    tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, nViews, p.perView, p.minOff, p.tw, p.th, l);
-  view_flag_kernel<<<nViews, 256, 0, s>>>(dst, p.perView, p.minOff, p.flagOff, p.tw * p.th);
+    tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, nViews, p.perView, p.badOff, p.tw, p.th, l);
+  view_flag_kernel<<<nViews, 256, 0, s>>>(dst, p.perView, p.badOff, p.flagOff, p.tw * p.th);
   return cudaGetLastError();
 }
 

@@ -207,7 +207,8 @@ class Context:
         out = (C.c_ulonglong * 16)()
         self._ck(self._lib.dmi_tsdf_tier_counters(self._h, out))
         return dict(zip(("t1_certified", "t2_entered", "t3_entered", "delta_guard", "units", "culled_brick_views",
-                         "near_band", "brick_views", "uniform_front", "far_front", "far_behind", "invalid_or_rejected"),
+                         "near_band", "brick_views", "uniform_front", "far_front", "far_behind", "invalid_or_rejected",
+                         "validity_only"),
                         [int(x) for x in out]))
 
     # -- coloration ------------------------------------------------------------------------------

@@ -173,7 +173,8 @@ int dmi_tsdf_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
  * [6] voxel*views in the FP64 band around the surface,
  * [8] voxel*views settled brick-wide as free space in front of the surface (one add per voxel),
  * [9] voxel*views classified far in front of the depth, [10] far behind it, [11] on an invalid pixel
- * (or rejected: behind the camera / outside the image) by the FP32 phase, [12..15] reserved (0).  Reading resets the counters. */
+ * (or rejected: behind the camera / outside the image) by the FP32 phase, [12] the part of [9] + [11] settled
+ * by the validity-only phase (bricks in front of every valid depth of their footprint), [13..15] reserved (0).  Reading resets the counters. */
 int dmi_tsdf_tier_counters(dmi_ctx* ctx, unsigned long long out[16]);
 
 /* ---- mesh coloration ----------------------------------------------------------------------- */
