@@ -542,6 +542,7 @@ int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, c
   if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
   if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
   DMI_REQUIRE(d_depths && d_cls && d_tileStats, "null argument");
+  DMI_REQUIRE((reinterpret_cast<uintptr_t>(d_tileStats) & 15) == 0, "d_tileStats must be 16-byte aligned");
   DMI_CK(cudaSetDevice(ctx->device));
   DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, d_cls, d_lo, clsSpareIndex,
                                    d_tileStats, ctx->stream));
@@ -564,6 +565,7 @@ int dmi_prepare_views_multi(dmi_ctx* ctx, int nViews, const double* d_depths, co
   for (int r = 0; r < nDst; r++)
   {
     DMI_REQUIRE(d_cls[r] && d_tileStats[r] && (!d_lo || d_lo[r]), "null destination");
+    DMI_REQUIRE((reinterpret_cast<uintptr_t>(d_tileStats[r]) & 15) == 0, "d_tileStats must be 16-byte aligned");
     dst.cls[r] = d_cls[r]; dst.lo[r] = d_lo ? d_lo[r] : nullptr; dst.tiles[r] = d_tileStats[r];
     bits |= reinterpret_cast<uintptr_t>(dst.cls[r]) | reinterpret_cast<uintptr_t>(dst.lo[r]);
   }
@@ -581,6 +583,7 @@ int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_dept
   if (!ctx->initialized || !ctx->vol_active) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_volume_begin has not been called");
   if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
   DMI_REQUIRE((d_depths || d_lo) && d_cls && d_tileStats && K && RT, "null argument");
+  DMI_REQUIRE((reinterpret_cast<uintptr_t>(d_tileStats) & 15) == 0, "d_tileStats must be 16-byte aligned");
   if (!fast_path_applies(ctx))
     return ctx->fail(DMI_ERR_BAD_PARAMETERS, "prepared views need the certified fast path (0 < Thick, finite parameters, kernel AUTO)");
   DMI_CK(cudaSetDevice(ctx->device));

@@ -132,7 +132,8 @@ int dmi_volume_end(dmi_ctx* ctx, void* h_scalar);
  *                                     double depth maps need not be exchanged or kept, 8 bytes per pixel
  *                                     carry everything (exact for |depth| >= 2^-64 or 0; smaller magnitudes
  *                                     keep 2^-117 absolute accuracy)
- *   d_tileStats  float[nViews][tileFloatsPerView]  tile statistics used by the brick tests
+ *   d_tileStats  float[nViews][tileFloatsPerView]  tile statistics used by the brick tests (16-byte aligned;
+ *                                     tileFloatsPerView is a multiple of 4)
  *   dmi_prepared_view_sizes    elements per view of d_cls / d_lo (W*H) and of d_tileStats
  *   dmi_prepare_views_device   fills the arrays (d_lo may be NULL); when clsSpareIndex >= 0,
  *                              d_cls[clsSpareIndex] is set to -1.0f
