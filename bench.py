@@ -264,6 +264,12 @@ def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
 
 # (workload, kernel, n_gpus) -> DRAM bytes per launch measured by ncu (mean of the two captured launches)
 NCU_DRAM_BYTES_PER_LAUNCH = {("config5", "auto", 1): 8.86e9}
+# same capture: the resource that actually binds the integration kernel is instruction issue
+NCU_ISSUE = {("config5", "auto", 1): {"issue_slots_busy": 0.651, "warps_eligible_per_cycle": 1.36, "fp64_pipe": 0.065, "fma_pipe": 0.243,
+                                       "alu_pipe": 0.490, "xu_pipe": 0.140, "lsu_pipe": 0.120, "l1_hit": 0.70, "l2_hit": 0.76,
+                                       "source": "ncu --set full, profiles/r1_tsdf_fast_config5_ncu_full.txt (smsp__issue_active, "
+                                                 "sm__inst_executed_pipe_*, fractions of peak); captured one kernel generation "
+                                                 "before the final one (238.6 ms per step)"}}
 EXCHANGE_TEXT = {"fused": "prepared by their owner straight into every rank's buffers: stores over NVLink from the preparation kernel",
                  "ce": "copy-engine pushes over CUDA IPC", "nccl": "NCCL all-gather"}
 _JSON_OUT = None
@@ -633,6 +639,7 @@ def main():
             # ncu --set full capture of this workload (profiles/r1_tsdf_fast_config5_ncu_full.txt); config5 only
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, args.kernel, world)),
             "traffic_unit": "bytes per launch (algorithmic: %.3g)" % (alg_bytes / max(kernel_launches, 1)),
+            "issue": NCU_ISSUE.get((args.workload, args.kernel, world)),
             "kernel": "tsdf_fast_kernel" if args.kernel != "exact" else "tsdf_exact_kernel",
             "definition": "28 algorithmic flops x the voxel*view pairs the kernel EVALUATED one by one (pairs settled by the exact "
                           "brick tests -- culled, or free space in front of the surface: one add -- are excluded) / summed CUDA-event time of the integration launches of the timed region",
