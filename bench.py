@@ -55,11 +55,12 @@ def parse_args():
     ap.add_argument("--no-coloration", action="store_true")
     ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
     ap.add_argument("--group", type=int, default=128, help="views per all-gather group (N>1)")
-    ap.add_argument("--exchange", default="ce", choices=["ce", "fused", "nccl"],
+    ap.add_argument("--exchange", default="ce", choices=["ce", "fused", "nccl", "nccl-split"],
                     help="N>1 view exchange: 'ce' = owner-side preparation + copy-engine pushes into CUDA-IPC mapped peer buffers (no SMs; "
                          "the fastest measured), 'fused' = the preparation kernel stores its outputs straight into every rank's mapped "
                          "buffers over NVLink (measured slower: SM stores reach ~230 GB/s and hold SMs the integration wants), "
-                         "'nccl' = all-gather of the double maps + preparation on every rank")
+                         "'nccl' = all-gather of the double maps + preparation on every rank, 'nccl-split' = owner-side preparation + "
+                         "NCCL all-gathers of the prepared arrays (not measured yet)")
     ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
                     help="N=1 diagnostic: integrate only the z-slab that RANK of WORLD would own (value counts that slab's pairs)")
     ap.add_argument("--quota", type=int, default=0, help="bricks per CTA of the integration kernel (0: 32 at N=1, 8 at N>1)")
@@ -270,7 +271,8 @@ NCU_ISSUE = {("config5", "auto", 1): {"issue_slots_busy": 0.651, "warps_eligible
                                        "source": "ncu --set full, profiles/r1_tsdf_fast_config5_ncu_full.txt (smsp__issue_active, "
                                                  "sm__inst_executed_pipe_*, fractions of peak); captured one kernel generation "
                                                  "before the final one (238.6 ms per step)"}}
-EXCHANGE_TEXT = {"fused": "prepared by their owner straight into every rank's buffers: stores over NVLink from the preparation kernel",
+EXCHANGE_TEXT = {"nccl-split": "owner-side preparation + NCCL all-gathers of the prepared arrays",
+                 "fused": "prepared by their owner straight into every rank's buffers: stores over NVLink from the preparation kernel",
                  "ce": "copy-engine pushes over CUDA IPC", "nccl": "NCCL all-gather"}
 _JSON_OUT = None
 
@@ -343,7 +345,7 @@ def main():
     noise = 0.25 * float(grid.spacing.max())
     all_depths, peer_ptr, own_ptr, fence = None, None, None, None
     cls_ptr = tile_ptr = None
-    if world > 1 and args.exchange in ("ce", "fused"):
+    if world > 1 and args.exchange in ("ce", "fused", "nccl-split"):
         # the resident view buffers are allocated by the library (plain cudaMalloc) so that every rank can map
         # every other rank's buffers through CUDA IPC and PUSH its share with the copy engines over NVLink.
         # One allocation: [residual i32 V*npix][classification f32, per group: n*npix + 4 spare][tile statistics f32];
@@ -368,6 +370,15 @@ def main():
         dist.all_gather_object(handles, ctx.ipc_get_handle(own_ptr))
         peer_ptr = [own_ptr if r == rank else ctx.ipc_open_handle(handles[r]) for r in range(world)]
         fence = torch.zeros(1, dtype=torch.float32, device=dev)
+
+        def _wrap(ptr, shape, typestr):
+            class _B:
+                pass
+            b = _B()
+            b.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+            return torch.as_tensor(b, device=dev)
+        cls_t = {g0: _wrap(cls_ptr + cls_off[g0] * 4, (g1 - g0, H, W), "<f4") for (g0, g1) in groups}
+        tiles_t = _wrap(tile_ptr, (V, ntile), "<f4")
         # the spare "invalid" slot after each group's classification images is written once, locally
         minus1 = torch.full((4,), -1.0, dtype=torch.float32, device=dev)      # (the slot right behind the group's images)
         for (g0, g1) in groups:
@@ -491,9 +502,12 @@ def main():
                             continue
                         ctx.prepare_views_device(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
                                                  cls_ptr + c_rel, -1, tile_ptr + a * ntile * 4, d_lo=own_ptr + a * npix * 4)
+                        if args.exchange == "nccl-split":
+                            ctx.set_stream(cur.cuda_stream)
+                            off += n
                         prepared = torch.cuda.Event()
                         prepared.record(comm_stream)
-                        for r in range(1, world):      # staggered order: every link busy, no hot receiver
+                        for r in range(1, world if args.exchange == "ce" else 1):      # staggered order: every link busy, no hot receiver
                             dst = (rank + r) % world
                             base = peer_ptr[dst]
                             ps = push_streams[r % len(push_streams)]      # several copies in flight at once
@@ -506,9 +520,15 @@ def main():
                             pushed = torch.cuda.Event()
                             pushed.record(ps)
                             comm_stream.wait_event(pushed)
-                        ctx.set_stream(cur.cuda_stream)
-                        off += n
-                    dist.all_reduce(fence)      # all shares of this group have landed everywhere
+                        if args.exchange == "ce":
+                            ctx.set_stream(cur.cuda_stream)
+                            off += n
+                    if args.exchange == "nccl-split":
+                        D.all_gather_group(dist, all_depths, g0, g1, rank, world)
+                        D.all_gather_group(dist, cls_t[g0], 0, g1 - g0, rank, world)
+                        D.all_gather_group(dist, tiles_t, g0, g1, rank, world)
+                    else:
+                        dist.all_reduce(fence)      # all shares of this group have landed everywhere
                 ev = torch.cuda.Event()
                 ev.record(comm_stream)
                 events.append(ev)
