@@ -507,3 +507,8 @@ def test_prepared_views_path_is_bit_identical(gpu_ctx):
     dn = d.cpu().numpy().reshape(-1)
     valid = hi != -1.0
     assert valid.any() and np.array_equal(rebuilt[valid], dn[valid])
+    # the device encoder against the host-side statement of the format (split_depth.py)
+    from cudadepthmapintegration_b200 import split_depth
+    hi_spec, lo_spec = split_depth.encode(dn, c.cpu().numpy().reshape(-1), 0.14)
+    assert np.array_equal(cls[:nv * npix].cpu().numpy().view(np.int32), hi_spec.view(np.int32))
+    assert np.array_equal(lo.cpu().numpy(), lo_spec)
