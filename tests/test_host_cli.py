@@ -39,6 +39,54 @@ def test_parsers_read_what_was_written(tmp_path):
         assert np.array_equal(K, s.K[v]) and np.array_equal(RT, s.RT[v])      # repr() round-trips doubles
 
 
+VTI_LAYOUTS = [dict(encoding="raw"), dict(encoding="ascii"), dict(encoding="base64"), dict(encoding="base64", compress=True),
+               dict(encoding="base64", compress=True, header_type="UInt64"), dict(encoding="binary"),
+               dict(encoding="binary", compress=True), dict(encoding="raw", compress=True, header_type="UInt64"),
+               dict(encoding="base64", header_with_data=True), dict(encoding="binary", header_with_data=True, header_type="UInt64")]
+
+
+def test_vti_reader_handles_the_xml_writers_layouts(tmp_path):
+    """ascii, inline base64, appended raw / base64, zlib blocks, 32- and 64-bit block headers, the byte count encoded
+    on its own or with the data: every view of the dataset uses another layout and must read back identically."""
+    _need_cli()
+    n = len(VTI_LAYOUTS)
+    s = Scene(8, n, 72, 50, rotate_deg=10.0)          # 72 x 50 x 8 B = 28.8 kB: less than one 32 kB zlib block ...
+    big = Scene(8, 1, 160, 120)                       # ... and 153.6 kB: several blocks with a ragged last one
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT, vti_options=VTI_LAYOUTS)
+    r = subprocess.run([CLI, "inspect", "--vti", str(tmp_path / "vtiList.txt"), "--krtd", str(tmp_path / "kList.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == f"views {n} krtd {n}"
+    for v, line in enumerate(lines[1:]):
+        t = line.split()
+        assert float(t[7]) == pytest.approx(float(s.depths[v].sum()), rel=1e-13), VTI_LAYOUTS[v]
+        assert float(t[9]) == pytest.approx(float(s.best_cost[v].sum()), rel=1e-13), VTI_LAYOUTS[v]
+        assert int(t[11]) == int(s.colors[v].astype(np.int64).sum()), VTI_LAYOUTS[v]
+        assert int(t[13]) == int((s.depths[v] == -1).sum()), VTI_LAYOUTS[v]
+    sub = tmp_path / "big"
+    dataset_io.write_dataset(str(sub), big.depths, big.best_cost, big.colors, big.K, big.RT,
+                             vti_options=[dict(encoding="base64", compress=True)])
+    r = subprocess.run([CLI, "inspect", "--vti", str(sub / "vtiList.txt"), "--krtd", str(sub / "kList.txt")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    t = r.stdout.strip().splitlines()[1].split()
+    assert float(t[7]) == pytest.approx(float(big.depths[0].sum()), rel=1e-13)
+    assert int(t[11]) == int(big.colors[0].astype(np.int64).sum())
+
+
+def test_vti_reader_reports_a_corrupt_block(tmp_path):
+    _need_cli()
+    s = Scene(8, 1, 40, 30)
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT, vti_options=[dict(encoding="base64", compress=True)])
+    f = tmp_path / "view_0000.vti"
+    data = f.read_bytes()
+    cut = data.index(b"_") + 40
+    f.write_bytes(data[:cut] + b"AAAA" + data[cut + 4:])          # damage the first compressed stream
+    r = subprocess.run([CLI, "inspect", "--vti", str(tmp_path / "vtiList.txt"), "--krtd", str(tmp_path / "kList.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "Depths" in r.stderr
+
+
 def test_cli_rejects_the_reference_cli_error_cases(tmp_path):
     _need_cli()
     base = [CLI, "reconstruction", "--gridOrigin", "-1", "-1", "-1", "--gridEnd", "1", "1", "1", "--gridDims", "9",
