@@ -31,6 +31,18 @@ class MeshColoration:
             else:
                 self._views = (colors, K[:colors.shape[0]], RT[:colors.shape[0]])
 
+    @classmethod
+    def from_files(cls, points, vti_list: str, krtd_list: str, device: int = 0):
+        """MeshColoration(vtkPolyData* mesh, std::string vtiList, std::string krtdList) (MeshColoration.cxx:52-72):
+        every listed view is read now, by the VTK-free readers of dataset_io."""
+        from . import dataset_io
+        try:
+            _, _, colors, K, RT = dataset_io.load_dataset(vti_list, krtd_list, need_color=True)
+        except (OSError, ValueError) as e:
+            print(f"Error, {e}", file=sys.stderr)
+            return cls(points, device=device)
+        return cls(points, colors, K, RT, device=device)
+
     def SetInput(self, points):
         """SetInput(vtkPolyData*): deep copy of the mesh (MeshColoration.cxx:85-91); vtkPoints keep their
         storage type (float32 by default)."""

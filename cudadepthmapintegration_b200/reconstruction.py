@@ -69,13 +69,26 @@ class CudaReconstructionFilter:
                       np.asarray(spacing, dtype=np.float64))
 
     def SetViews(self, depths, best_cost, K, RT):
-        """Stands for SetFilePathVTI / SetFilePathKRTD: the content of the listed files, in list order."""
+        """In-memory form of SetFilePathVTI / SetFilePathKRTD: the content of the listed files, in list order."""
         self._views = (depths, best_cost, np.asarray(K, dtype=np.float64), np.asarray(RT, dtype=np.float64))
+
+    # vtkSetMacro(FilePathKRTD / FilePathVTI, std::string), vtkCudaReconstructionFilter.h:75-77: the list files are read
+    # at Update() by the VTK-free readers of dataset_io (help::ExtractAllFilePath, ReadKrtdFile, the .vti point arrays)
+    def SetFilePathKRTD(self, path): self.FilePathKRTD = str(path)
+    def SetFilePathVTI(self, path): self.FilePathVTI = str(path)
 
     def Update(self) -> int:
         """RequestData (.cxx:96-151): returns 1 on success, 0 on the reference's error paths."""
         self.ExecutionTime = -1.0
         start = time.perf_counter()
+        if self._views is None and getattr(self, "FilePathKRTD", "") and getattr(self, "FilePathVTI", ""):
+            from . import dataset_io
+            try:
+                d, c, _, K, RT = dataset_io.load_dataset(self.FilePathVTI, self.FilePathKRTD)
+            except (OSError, ValueError) as e:
+                print(f"Error : {e}", file=sys.stderr)
+                return 0
+            self._views = (d, c, K, RT)
         if self._views is None or self._grid is None:
             print("Error, some inputs have not been set.", file=sys.stderr)
             return 0

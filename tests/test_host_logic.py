@@ -94,3 +94,24 @@ def test_render_views_do_not_depend_on_the_batch():
         d1, c1, col1 = syn.render_views(K[i:i + 1], RT[i:i + 1], 96, 72, first_view=i, depth_noise=0.01)
         assert np.array_equal(d1[0].numpy(), d[i].numpy()) and np.array_equal(c1[0].numpy(), c[i].numpy())
         assert np.array_equal(col1[0].numpy(), col[i].numpy())
+
+
+def test_python_readers_round_trip_every_vti_layout(tmp_path):
+    """dataset_io.load_dataset (what SetFilePathVTI / SetFilePathKRTD and MeshColoration.from_files use) reads back,
+    bit for bit, datasets written in every layout VTK's XML writers produce."""
+    from cudadepthmapintegration_b200 import dataset_io
+    from tests.scenes import Scene
+    from tests.test_host_cli import VTI_LAYOUTS
+    s = Scene(8, len(VTI_LAYOUTS), 72, 50, rotate_deg=10.0)
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT, vti_options=VTI_LAYOUTS)
+    d, c, col, K, RT = dataset_io.load_dataset(str(tmp_path / "vtiList.txt"), str(tmp_path / "kList.txt"), need_color=True)
+    assert np.array_equal(d, s.depths) and np.array_equal(c, s.best_cost) and np.array_equal(col, s.colors)
+    assert np.array_equal(K, s.K) and np.array_equal(RT, s.RT)
+    # fewer .krtd than .vti entries is the reference's error case
+    (tmp_path / "short.txt").write_text("view_0000.krtd\n")
+    with pytest.raises(ValueError):
+        dataset_io.load_dataset(str(tmp_path / "vtiList.txt"), str(tmp_path / "short.txt"))
+    # list-file tokenisation: the last blank-separated token, relative to the list's directory
+    (tmp_path / "odd.txt").write_text("0 a.vti\nb.vti \n\nc d  \n")
+    got = dataset_io.extract_all_file_path(str(tmp_path / "odd.txt"))
+    assert got == [str(tmp_path) + "/a.vti", str(tmp_path) + "/b.vti", str(tmp_path) + "/"]

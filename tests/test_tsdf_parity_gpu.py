@@ -390,6 +390,32 @@ def test_filter_class_mirrors_reference_api(oracle):
     f.close()
 
 
+def test_filter_class_reads_the_reference_file_layout(tmp_path, oracle):
+    """SetFilePathVTI / SetFilePathKRTD (vtkCudaReconstructionFilter.h:75-77): list files, .krtd and .vti (appended
+    base64 + zlib, the XML writers' default) read by the VTK-free readers give the same volume as in-memory views."""
+    from cudadepthmapintegration_b200 import CudaReconstructionFilter, dataset_io
+    s = Scene(20, 4, 48, 36)
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT,
+                             vti_options=[dict(encoding="base64", compress=True), dict(encoding="raw")])
+    f = CudaReconstructionFilter()
+    f.SetInputGrid(s.grid.point_dims, s.grid.origin, s.grid.spacing)
+    f.SetGridMatrix(s.grid.matrix)
+    f.SetFilePathVTI(str(tmp_path / "vtiList.txt")); f.SetFilePathKRTD(str(tmp_path / "kList.txt"))
+    f.SetRayPotentialThickness(s.rp.thick); f.SetRayPotentialRho(s.rp.rho)
+    f.SetRayPotentialEta(s.rp.eta); f.SetRayPotentialDelta(s.rp.delta)
+    f.SetThresholdBestCost(0.14)
+    assert f.Update() == 1
+    want = oracle.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
+    assert_close(f.GetOutput().reshape(-1), want)
+    f.close()
+    g = CudaReconstructionFilter()
+    g.SetInputGrid(s.grid.point_dims, s.grid.origin, s.grid.spacing)
+    g.SetFilePathVTI(str(tmp_path / "missing.txt")); g.SetFilePathKRTD(str(tmp_path / "kList.txt"))
+    g.SetRayPotentialThickness(s.rp.thick); g.SetRayPotentialRho(s.rp.rho)
+    assert g.Update() == 0                                      # unreadable list -> the reference's error path
+    g.close()
+
+
 # ---- BASELINE.json sizes: size-independent properties (the oracle would take hours here) --------------
 
 def _device_scene(n, n_views, W, H):
