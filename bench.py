@@ -377,8 +377,10 @@ def main():
             b = _B()
             b.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
             return torch.as_tensor(b, device=dev)
-        cls_t = {g0: _wrap(cls_ptr + cls_off[g0] * 4, (g1 - g0, H, W), "<f4") for (g0, g1) in groups}
-        tiles_t = _wrap(tile_ptr, (V, ntile), "<f4")
+        cls_t, tiles_t = {}, None
+        if args.exchange == "nccl-split":
+            cls_t = {g0: _wrap(cls_ptr + cls_off[g0] * 4, (g1 - g0, H, W), "<f4") for (g0, g1) in groups}
+            tiles_t = _wrap(tile_ptr, (V, ntile), "<f4")
         # the spare "invalid" slot after each group's classification images is written once, locally
         minus1 = torch.full((4,), -1.0, dtype=torch.float32, device=dev)      # (the slot right behind the group's images)
         for (g0, g1) in groups:
