@@ -61,6 +61,8 @@ _PROTOTYPES = {
     "dmi_volume_end": (C.c_int, [_vp, _vp]),
     "dmi_prepared_view_sizes": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "dmi_prepare_views_device": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp, _ll, _vp]),
+    "dmi_plan_tile_grid": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dmi_plan_slab_tile_intervals": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "dmi_prepare_views_multi": (C.c_int, [_vp, _i, _vp, _vp, _d, _i, _vp, _vp, _ll, _vp]),
     "dmi_volume_integrate_prepared": (C.c_int, [_vp, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
     "dmi_volume_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),

@@ -597,6 +597,117 @@ int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_dept
   return DMI_OK;
 }
 
+// ---- which part of a view does a z-slab need? (host only; planning of cropped view exchanges) --------------
+// The image of the slab's box under a view is the convex hull of its 8 projected corners (all in front of the
+// camera); per row of 8x8-pixel tiles the hull covers one interval of tile columns.
+
+namespace {
+
+struct P2 { double x, y; };
+
+double cross2(const P2& o, const P2& a, const P2& b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); }
+
+// Andrew's monotone chain; returns the hull counter-clockwise, without the repeated first point
+std::vector<P2> convex_hull(std::vector<P2> p)
+{
+  std::sort(p.begin(), p.end(), [](const P2& a, const P2& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+  std::vector<P2> h(2 * p.size());
+  size_t k = 0;
+  for (size_t i = 0; i < p.size(); i++) { while (k >= 2 && cross2(h[k - 2], h[k - 1], p[i]) <= 0) k--; h[k++] = p[i]; }
+  for (size_t i = p.size() - 1, t = k + 1; i > 0; i--) { while (k >= t && cross2(h[k - 2], h[k - 1], p[i - 1]) <= 0) k--; h[k++] = p[i - 1]; }
+  h.resize(k > 1 ? k - 1 : k);
+  return h;
+}
+
+}  // namespace
+
+#define DMI_PLAN_REQUIRE(cond, msg) do { if (!(cond)) { g_create_error = msg; return DMI_ERR_INVALID_ARGUMENT; } } while (0)
+
+int dmi_plan_tile_grid(const int depthMapDims[2], int* tilesPerRow, int* tileRows)
+{
+  DMI_PLAN_REQUIRE(depthMapDims && depthMapDims[0] >= 1 && depthMapDims[1] >= 1, "depth map dims must be >= 1");
+  const dmi::TilePyramid p = dmi::tile_pyramid_layout(depthMapDims[0], depthMapDims[1]);
+  if (tilesPerRow) *tilesPerRow = p.tw;
+  if (tileRows) *tileRows = p.th;
+  return DMI_OK;
+}
+
+int dmi_plan_slab_tile_intervals(const double gridMatrix[16], const int gridDims[3], const double gridOrig[3],
+                                 const double gridSpacing[3], const int depthMapDims[2], int nViews, const double* K,
+                                 const double* RT, int k0, int k1, short* firstTile, short* lastTile)
+{
+  DMI_PLAN_REQUIRE(gridMatrix && gridDims && gridOrig && gridSpacing && depthMapDims, "null argument");
+  DMI_PLAN_REQUIRE(nViews >= 0 && K && RT && firstTile && lastTile, "null argument");
+  DMI_PLAN_REQUIRE(gridDims[0] >= 2 && gridDims[1] >= 2 && gridDims[2] >= 2, "grid point dims must be >= 2 (at least one cell)");
+  DMI_PLAN_REQUIRE(depthMapDims[0] >= 1 && depthMapDims[1] >= 1, "depth map dims must be >= 1");
+  dmi::GridParams g{};
+  memcpy(g.gm, gridMatrix, sizeof(double) * 12);
+  for (int a = 0; a < 3; a++) { g.orig[a] = gridOrig[a]; g.sp[a] = gridSpacing[a]; }
+  g.Nx = gridDims[0] - 1; g.Ny = gridDims[1] - 1; g.Nz = gridDims[2] - 1;
+  g.W = depthMapDims[0]; g.H = depthMapDims[1];
+  DMI_PLAN_REQUIRE(0 <= k0 && k0 <= k1 && k1 <= g.Nz, "slab must satisfy 0 <= k0 <= k1 <= Nz");
+  const dmi::TilePyramid lay = dmi::tile_pyramid_layout(g.W, g.H);
+  const int tw = lay.tw, th = lay.th;
+  DMI_PLAN_REQUIRE(tw < 32768, "image too wide for 16-bit tile columns");
+  const double margin = 2.0;      // pixels: rounding to the nearest pixel (0.5) + slack for the arithmetic
+  for (int v = 0; v < nViews; v++)
+  {
+    short* f = firstTile + (size_t)v * th;
+    short* l = lastTile + (size_t)v * th;
+    for (int r = 0; r < th; r++) { f[r] = 1; l[r] = 0; }                 // empty
+    if (k0 == k1) continue;
+    const double* k16 = K + 16 * (size_t)v;
+    const double* rt = RT + 16 * (size_t)v;
+    std::vector<P2> pts;
+    bool behind = false;
+    for (int c = 0; c < 8 && !behind; c++)
+    {
+      // box corners in cell-index space: voxel centres (idx + 0.5) lie inside [0, N] x [0, N] x [k0, k1]
+      const double gx = g.orig[0] + ((c & 1) ? g.Nx : 0) * g.sp[0];
+      const double gy = g.orig[1] + ((c & 2) ? g.Ny : 0) * g.sp[1];
+      const double gz = g.orig[2] + ((c & 4) ? k1 : k0) * g.sp[2];
+      double w[3], cam[3], h[3];
+      for (int a = 0; a < 3; a++) w[a] = g.gm[4 * a] * gx + g.gm[4 * a + 1] * gy + g.gm[4 * a + 2] * gz + g.gm[4 * a + 3];
+      for (int a = 0; a < 3; a++) cam[a] = rt[4 * a] * w[0] + rt[4 * a + 1] * w[1] + rt[4 * a + 2] * w[2] + rt[4 * a + 3];
+      for (int a = 0; a < 3; a++) h[a] = k16[4 * a] * cam[0] + k16[4 * a + 1] * cam[1] + k16[4 * a + 2] * cam[2] + k16[4 * a + 3];
+      if (!(h[2] > 1e-9 * (std::fabs(h[0]) + std::fabs(h[1]) + 1.0))) behind = true;      // also catches NaN
+      else pts.push_back(P2{h[0] / h[2], h[1] / h[2]});
+    }
+    if (behind)
+    {
+      // the box reaches the camera plane: its image is unbounded, every tile may be needed
+      for (int r = 0; r < th; r++) { f[r] = 0; l[r] = (short)(tw - 1); }
+      continue;
+    }
+    const std::vector<P2> hull = convex_hull(pts);
+    const size_t n = hull.size();
+    for (int r = 0; r < th; r++)
+    {
+      // storage rows 8r .. 8r+7 are image rows py = H-1-row (CudaReconstruction.cu:141-149)
+      const double ylo = (double)(g.H - 1 - std::min(8 * r + 7, g.H - 1)) - margin, yhi = (double)(g.H - 1 - 8 * r) + margin;
+      double xmin = INFINITY, xmax = -INFINITY;
+      for (size_t q = 0; q < n; q++)
+      {
+        const P2 a = hull[q], b = hull[(q + 1) % n];
+        if (a.y >= ylo && a.y <= yhi) { xmin = std::min(xmin, a.x); xmax = std::max(xmax, a.x); }
+        for (const double yl : {ylo, yhi})
+          if ((a.y - yl) * (b.y - yl) < 0)                   // the edge crosses this boundary line
+          {
+            const double x = a.x + (b.x - a.x) * (yl - a.y) / (b.y - a.y);
+            xmin = std::min(xmin, x); xmax = std::max(xmax, x);
+          }
+      }
+      if (n == 1 && hull[0].y >= ylo && hull[0].y <= yhi) { xmin = xmax = hull[0].x; }
+      if (!(xmin <= xmax)) continue;
+      xmin -= margin; xmax += margin;
+      if (xmax < 0.0 || xmin > (double)(g.W - 1)) continue;
+      const int c0 = std::max(0, (int)std::floor(xmin / 8.0)), c1 = std::min(tw - 1, (int)std::floor(xmax / 8.0));
+      if (c0 <= c1) { f[r] = (short)c0; l[r] = (short)c1; }
+    }
+  }
+  return DMI_OK;
+}
+
 int dmi_volume_integrate_host(dmi_ctx* ctx, int nViews, const double* depths, const double* bestCost,
                               double thresholdBestCost, const double* K, const double* RT)
 {

@@ -278,3 +278,27 @@ class Context:
         t = C.c_double()
         self._ck(self._lib.dmi_measure_fp_peak(self._h, int(which), float(ms_target), C.byref(t)))
         return float(t.value)
+
+
+def plan_slab_tile_intervals(grid_matrix, point_dims, origin, spacing, depth_map_dims, K, RT, k0: int, k1: int):
+    """Which 8x8-pixel tiles (storage rows) of each view can z-slab [k0, k1) gather from?  Returns (first, last),
+    int16 [n_views, tile_rows]: the inclusive interval of tile columns per tile row, first > last = empty row.
+    Pure host planning (dmi_plan_slab_tile_intervals): needs the library, not a GPU."""
+    lib = _lib.load()
+    gm = _f64(grid_matrix, 16)
+    pd = np.ascontiguousarray(point_dims, dtype=np.int32)
+    og, sp = _f64(origin), _f64(spacing)
+    dd = np.ascontiguousarray(depth_map_dims, dtype=np.int32)
+    K = _f64(K, 16); RT = _f64(RT, 16)
+    n = K.size // 16
+    tw, th = C.c_int(), C.c_int()
+    rc = lib.dmi_plan_tile_grid(_ptr(dd), C.byref(tw), C.byref(th))
+    if rc != 0:
+        raise DmiError(rc, (lib.dmi_last_error(None) or b"").decode())
+    first = np.empty((n, th.value), dtype=np.int16)
+    last = np.empty((n, th.value), dtype=np.int16)
+    rc = lib.dmi_plan_slab_tile_intervals(_ptr(gm), _ptr(pd), _ptr(og), _ptr(sp), _ptr(dd), n, _ptr(K), _ptr(RT), int(k0), int(k1),
+                                          _ptr(first), _ptr(last))
+    if rc != 0:
+        raise DmiError(rc, (lib.dmi_last_error(None) or b"").decode())
+    return first, last

@@ -155,6 +155,17 @@ int dmi_prepare_views_multi(dmi_ctx* ctx, int nViews, const double* d_depths, co
 int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo,
                                   const float* d_cls, long long clsSpareIndex, const float* d_tileStats,
                                   const double* K, const double* RT);
+/* Planning of cropped view exchanges (pure host functions: no context, no GPU): a rank only needs the part of a
+ * view that the box of its z-slab projects onto.  Grid and image arguments as in dmi_initialize.  Tiles are 8 x 8
+ * pixels of STORAGE rows (bottom-up images); the grid has tilesPerRow x tileRows tiles.  For slab [k0, k1) and each
+ * view, firstTile / lastTile [nViews][tileRows] receive the inclusive interval of tile columns of every tile row
+ * that some voxel centre of the slab can round into (2-pixel margin); firstTile > lastTile marks an empty row.  A
+ * view whose camera plane cuts the box gets every tile.  Errors: dmi_last_error(NULL). */
+int dmi_plan_tile_grid(const int depthMapDims[2], int* tilesPerRow, int* tileRows);
+int dmi_plan_slab_tile_intervals(const double gridMatrix[16], const int gridDims[3], const double gridOrig[3],
+                                 const double gridSpacing[3], const int depthMapDims[2], int nViews, const double* K,
+                                 const double* RT, int k0, int k1, short* firstTile, short* lastTile);
+
 /* Device address and size in bytes of the slab (valid between begin and the next begin/destroy). */
 int dmi_volume_device_ptr(dmi_ctx* ctx, void** d_ptr, size_t* bytes);
 
