@@ -19,10 +19,13 @@
  * x86-64 `int = std::round(double)` is cvttsd2si: NaN / +-inf / out-of-range -> INT_MIN, which the
  * `< 0` test at MeshColoration.cxx:158 then rejects.
  *
- * PARITY UNPINNED by reference tests (there are none).  Pinned instead by the
- * hand-derived known answers in tests/test_oracle_kats.py and, when built, by the reference's own
- * MeshColoration.cxx compiled against the minimal VTK stand-in under oracle/vtk_shim/
- * (oracle/_ref/libref_coloration.so, see oracle/Makefile).
+ * PINNED: the reference ships no tests, so this file is pinned against the reference's own
+ * code instead -- Coloration/MeshColoration.cxx, Sources/ReconstructionData.cxx and Sources/Helper.h compiled
+ * unmodified against the VTK stand-in of oracle/vtk_shim/ (oracle/_ref/libref_coloration.so, oracle/Makefile):
+ * bit-identical NbProjectedDepthMap / MedianColoration / MeanColoration on the cases of
+ * tests/test_coloration_pinning.py (general 3x3 K, points behind cameras, 0/0, inf/NaN points, x.5 pixel
+ * boundaries, float32 and float64 points), golden arrays in tests/golden/color_golden.npz, plus the hand-derived
+ * known answers of tests/test_oracle_kats.py.  What the stand-in restates of VTK (un-vendored) is listed above.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
  * Build: gcc -O2 -ffp-contract=off -fopenmp.

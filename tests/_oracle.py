@@ -185,6 +185,50 @@ def _load_ref(name, cls):
     return cls(C.CDLL(path))
 
 
+class RefColoration:
+    """The reference's own MeshColoration.cxx / ReconstructionData.cxx / Helper.h compiled against the VTK stand-in
+    (oracle/ref_coloration_harness.cpp -> oracle/_ref/libref_coloration.so)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.ref_coloration_run.restype = C.c_int
+        lib.ref_coloration_run.argtypes = [C.c_char_p, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]
+        lib.ref_world_to_pixel.restype = C.c_int
+        lib.ref_world_to_pixel.argtypes = [C.c_char_p, _vp, _vp, _vp, _vp]
+
+    def colorize(self, xyz, colors, K, RT, W, H):
+        import tempfile
+        xyz = np.ascontiguousarray(xyz)
+        assert xyz.dtype in (np.float32, np.float64)
+        P = xyz.size // 3
+        K = _f64(K); RT = _f64(RT)
+        n = K.size // 16
+        colors = np.ascontiguousarray(colors, dtype=np.uint8)
+        assert colors.size == n * W * H * 3
+        mean = np.zeros((P, 3), dtype=np.uint8)
+        median = np.zeros((P, 3), dtype=np.uint8)
+        nb = np.zeros(P, dtype=np.int32)
+        with tempfile.TemporaryDirectory(prefix="dmi_refcolor_") as d:
+            rc = self.lib.ref_coloration_run(d.encode(), P, _p(xyz), F64 if xyz.dtype == np.float64 else F32, n, _p(colors),
+                                             _p(K), _p(RT), W, H, _p(mean), _p(median), _p(nb))
+        if rc != 0:
+            raise RuntimeError(f"reference coloration harness failed ({rc})")
+        return mean, median, nb
+
+    def world_to_pixel(self, K4, RT4, p):
+        import tempfile
+        out = np.zeros(2, dtype=np.int32)
+        with tempfile.TemporaryDirectory(prefix="dmi_refcolor_") as d:
+            rc = self.lib.ref_world_to_pixel(d.encode(), _p(_f64(K4)), _p(_f64(RT4)), _p(_f64(p)), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"reference coloration harness failed ({rc})")
+        return int(out[0]), int(out[1])
+
+
+def load_ref_coloration():
+    return _load_ref("libref_coloration.so", RefColoration)
+
+
 def load_ref_host():
     return _load_ref("libref_tsdf_host.so", RefHost)
 

@@ -28,6 +28,15 @@ def ref_host():
 
 
 @pytest.fixture(scope="session")
+def ref_coloration():
+    from tests import _oracle
+    lib = _oracle.load_ref_coloration()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref_coloration.so not built (reference tree absent)")
+    return lib
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx():
     import torch
     if not torch.cuda.is_available():

@@ -1,6 +1,9 @@
 """Generates tests/golden/tsdf_golden.npz by running the REFERENCE'S OWN kernel text (compiled for the
 host by oracle/Makefile into oracle/_ref/libref_tsdf_host.so) on the seeded scenes of
-tests/test_oracle_pinning.py.  Needs /root/reference (to build oracle/_ref); the fixtures it writes do not.
+tests/test_oracle_pinning.py, and tests/golden/color_golden.npz by running the reference's own
+MeshColoration.cxx / ReconstructionData.cxx / Helper.h (oracle/_ref/libref_coloration.so, built against the VTK
+stand-in of oracle/vtk_shim/) on the cases of tests/test_coloration_pinning.py.
+Needs /root/reference (to build oracle/_ref); the fixtures it writes do not.
 
     python tests/golden/make_golden.py
 """
@@ -29,6 +32,17 @@ def main():
         print(name, out[name].dtype, out[name].shape, "nonzero:", np.count_nonzero(out[name]),
               "sum:", float(out[name].astype(np.float64).sum()))
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tsdf_golden.npz"), **out)
+
+    from tests import test_coloration_pinning as tcp
+    refc = _oracle.load_ref_coloration()
+    if refc is None:
+        raise SystemExit("oracle/_ref/libref_coloration.so unavailable (no reference tree?)")
+    cout = {}
+    for name in sorted(tcp.CASES):
+        pts, colors, K, RT, W, H = tcp.CASES[name]()
+        cout[name] = tcp.pack(*refc.colorize(pts, colors, K, RT, W, H))
+        print(name, cout[name].shape, "seen:", int((cout[name][:, 6] > 0).sum()), "max views:", int(cout[name][:, 6].max()))
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "color_golden.npz"), **cout)
 
 
 if __name__ == "__main__":

@@ -55,13 +55,37 @@ def test_double_points_behind_camera_and_degenerate(gpu_ctx, oracle):
     assert (want[2][:9] <= 8).all()
 
 
-def test_no_point_seen_keeps_zero_fill(gpu_ctx):
-    s = Scene(8, 3, 32, 24)
-    pts = np.full((64, 3), 1000.0, dtype=np.float32)
-    pts[:, 0] += np.arange(64)
-    mean, med, nb = gpu_ctx.colorize(pts, s.colors, s.K, s.RT, s.W, s.H)
-    # these points project near the image centre?  no: they are far off-axis for every camera
-    assert mean.shape == (64, 3) and nb.shape == (64,)
+def test_no_point_seen_keeps_zero_fill(gpu_ctx, oracle):
+    # points no view sees keep 0/0/0 and count 0 (MeshColoration.cxx:116-118,124-126,132,174)
+    W, H = 32, 24
+    K = np.eye(4); K[0, 0] = K[1, 1] = 24.0; K[0, 2] = W / 2; K[1, 2] = H / 2
+    K = np.repeat(K.reshape(1, 16), 3, axis=0); RT = np.repeat(np.eye(4).reshape(1, 16), 3, axis=0)
+    colors = np.full((3, H, W, 3), 200, dtype=np.uint8)
+    pts = np.zeros((70, 3), dtype=np.float32)
+    pts[:, 0] = 50.0 + np.arange(70)                    # u = 24 * x + 16 >= 1216: outside every image
+    pts[:, 2] = 1.0
+    pts[64] = [0.0, 0.0, 1.0]                           # one seen point in the middle of the batch
+    mean, med, nb = gpu_ctx.colorize(pts, colors, K, RT, W, H)
+    unseen = np.arange(70) != 64
+    assert (nb[unseen] == 0).all() and (mean[unseen] == 0).all() and (med[unseen] == 0).all()
+    assert nb[64] == 3 and mean[64].tolist() == [200, 200, 200] and med[64].tolist() == [200, 200, 200]
+    want = oracle.colorize(pts, colors, K, RT, W, H)
+    check((mean, med, nb), want)
+
+
+@pytest.mark.parametrize("name", ["sphere10", "even_odd_random_points", "double_points_behind_cameras", "general_k",
+                                  "pixel_boundaries"])
+def test_gpu_matches_reference_coloration_and_golden(gpu_ctx, name):
+    """Against the reference's OWN MeshColoration.cxx (oracle/_ref/libref_coloration.so, prebuilt where /root/reference
+    exists) and against the golden arrays it produced; a general 3x3 K, x.5 pixel boundaries and float64 points included."""
+    import os
+    from tests import _oracle, test_coloration_pinning as tcp
+    pts, colors, K, RT, W, H = tcp.CASES[name]()
+    got = gpu_ctx.colorize(pts, colors, K, RT, W, H)
+    assert np.array_equal(tcp.pack(*got), np.load(tcp.GOLDEN)[name])
+    ref = _oracle.load_ref_coloration()
+    if ref is not None:
+        check(got, ref.colorize(pts, colors, K, RT, W, H))
 
 
 def test_mesh_coloration_class(oracle):
