@@ -380,8 +380,10 @@ static bool fast_path_applies(const dmi_ctx* ctx)
   // parameters; Reconstruction/main.cxx:270-271) and pixel / voxel coordinates that floats hold
   // exactly; anything else goes through the exact kernel.
   const dmi::GridParams& g = ctx->g;
+  // Delta >= 0: the brick tests and phase C compare |diff| with Delta + margin, which is only the reference's
+  // `a > Delta` for a non-negative Delta (for Delta < 0 the reference always takes its first branch)
   return ctx->opt_kernel == DMI_TSDF_KERNEL_AUTO && g.thick > 0 && std::isfinite(g.rho_over_thick) &&
-         std::isfinite(g.delta) && std::isfinite(g.neg_eta_rho) && std::isfinite(g.rho) && g.W < (1 << 21) &&
+         std::isfinite(g.delta) && g.delta >= 0 && std::isfinite(g.neg_eta_rho) && std::isfinite(g.rho) && g.W < (1 << 21) &&
          g.H < (1 << 21) && g.Nx < (1 << 23) && g.Ny < (1 << 23) && g.Nz < (1 << 23);
 }
 
@@ -419,6 +421,13 @@ static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_dep
   const size_t tilesPerView = (size_t)dmi::tile_pyramid_layout(g.W, g.H).perView;
   int chunk = dmi::kFastChunk;
   if (ctx->opt_chunk > 0 && ctx->opt_chunk < chunk) chunk = (int)ctx->opt_chunk;
+  // the kernel addresses the spare -1.0f slot as a 32-bit offset from the last storage row of each view
+  {
+    const long long lastRow = (long long)(g.H - 1) * g.W;
+    const long long hi = clsSpare - lastRow, lo = clsSpare - ((long long)npix * (nViews - 1) + lastRow);
+    DMI_REQUIRE(hi <= 2147483647ll && lo >= -2147483647ll,
+                "the spare classification slot must lie within 2^31 floats of every view of the call: split the call");
+  }
   DMI_CK(ctx->viewscratch.ensure(sizeof(dmi::ViewFast) * dmi::kFastChunk));
   DMI_CK(ctx->maskscratch.ensure(dmi::tsdf_fast_mask_bytes(g)));
   dmi::FastChunk* c = &ctx->fast_chunk;
@@ -885,6 +894,7 @@ int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyz
   DMI_CK(cudaSetDevice(ctx->device));
   dmi::ColorViews views;
   DMI_REQUIRE(W < (1 << 21) && H < (1 << 21), "image dims must be below 2^21");
+  DMI_REQUIRE((long long)W * H < (1ll << 31), "image too large for the 32-bit pixel index");
   int rc = pack_color_views(ctx, nViews, K, RT, W, H, &views);
   if (rc != DMI_OK) return rc;
   EventSpan span = ctx->color_stats.open();
@@ -906,6 +916,7 @@ int dmi_colorize(dmi_ctx* ctx, size_t nPoints, const void* xyz, int xyzType, int
   DMI_REQUIRE(xyzType == DMI_F32 || xyzType == DMI_F64, "xyzType must be DMI_F32 or DMI_F64");
   DMI_REQUIRE(W >= 1 && H >= 1, "image dims must be >= 1");
   DMI_REQUIRE(K && RT && colors, "null argument");
+  DMI_REQUIRE((long long)W * H < (1ll << 31), "image too large for the 32-bit pixel index");
   if (nPoints == 0) return DMI_OK;
   DMI_REQUIRE(xyz && mean && median && nbProjected, "null argument");
   DMI_CK(cudaSetDevice(ctx->device));

@@ -44,7 +44,9 @@ public:
     hasGrid_ = true;
   }
 
-  // RequestData (.cxx:96-151): 1 on success, 0 on the reference's error paths
+  // RequestData (.cxx:96-151): 1 on success, 0 on the reference's error paths.  The reference ignores Compute()'s
+  // result (.cxx:144) and would hand on a zero volume after a failed read; here a failed Compute() (unreadable or
+  // corrupt file, size mismatch, CUDA / dmi error) makes Update() return 0 and leaves no output to write.
   int Update()
   {
     ExecutionTime = -1;
@@ -62,7 +64,7 @@ public:
       std::cerr << "Error : Ray potential Rho or Thickness or both have not been set" << std::endl;
       return 0;
     }
-    Compute();
+    if (Compute() != 0) { Output.clear(); return 0; }
     ExecutionTime = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     return 1;
   }

@@ -164,7 +164,8 @@ inline bool DecodeBlock(const char* p, size_t avail, bool base64, bool zlibCompr
   {
     const uint64_t cs = HeaderWord(head.data() + (3 + b) * hs, hdr64);
     const uint64_t us = (b + 1 == nb && lastSize) ? lastSize : blockSize;
-    if (in + cs > dataAvail || off + us > want) { why = "corrupt compression header"; return false; }
+    // sizes come from the file: written so that no sum of them can wrap
+    if (cs > dataAvail - in || us > want - off) { why = "corrupt compression header"; return false; }
     uLongf got = (uLongf)us;
     if (uncompress(out.data() + off, &got, data + in, (uLong)cs) != Z_OK || got != us) { why = "zlib could not inflate a block"; return false; }
     in += cs; off += us;
@@ -238,8 +239,9 @@ inline bool ReadVti(const std::string& path, DepthMapImage& img, std::string& er
       {
         const size_t de = s.find("</DataArray>", te);
         std::istringstream iss(s.substr(te + 1, de - te - 1));
-        if (isColor) { bytes.resize(count); for (size_t i = 0; i < count; i++) { int v = 0; iss >> v; bytes[i] = (uint8_t)v; } }
-        else { vals.resize(count); for (size_t i = 0; i < count; i++) iss >> vals[i]; }
+        if (isColor) { bytes.resize(count); for (size_t i = 0; i < count && iss; i++) { int v = 0; iss >> v; bytes[i] = (uint8_t)v; } }
+        else { vals.resize(count); for (size_t i = 0; i < count && iss; i++) iss >> vals[i]; }
+        if (iss.fail()) { err = path + ": ascii array '" + name + "' is truncated or malformed"; return false; }
       }
       else if (format == "appended" || format == "binary")
       {

@@ -87,6 +87,21 @@ def test_vti_reader_reports_a_corrupt_block(tmp_path):
     assert r.returncode != 0 and "Depths" in r.stderr
 
 
+def test_vti_reader_rejects_a_truncated_ascii_array(tmp_path):
+    _need_cli()
+    s = Scene(8, 1, 40, 30)
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT, vti_options=[dict(encoding="ascii")])
+    f = tmp_path / "view_0000.vti"
+    text = f.read_text()
+    a = text.index(">", text.index('Name="Depths"')) + 1
+    b = text.index("</DataArray>", a)
+    vals = text[a:b].split()
+    f.write_text(text[:a] + " ".join(vals[:len(vals) // 2]) + " garbage " + text[b:])       # half the values, then junk
+    r = subprocess.run([CLI, "inspect", "--vti", str(tmp_path / "vtiList.txt"), "--krtd", str(tmp_path / "kList.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "Depths" in r.stderr
+
+
 def test_cli_rejects_the_reference_cli_error_cases(tmp_path):
     _need_cli()
     base = [CLI, "reconstruction", "--gridOrigin", "-1", "-1", "-1", "--gridEnd", "1", "1", "1", "--gridDims", "9",
@@ -121,6 +136,17 @@ def test_cli_end_to_end_against_oracle(tmp_path, oracle):
     want = oracle.tsdf_integrate(grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, np.zeros(24 ** 3))
     assert np.array_equal(got != 0, want != 0)
     assert np.abs(got - want).max() <= 1e-6
+    # a corrupt depth map must not leave a valid-looking all-zero volume behind with exit code 0
+    bad = tmp_path / "bad"
+    dataset_io.write_dataset(str(bad), s.depths, s.best_cost, s.colors, s.K, s.RT, vti_options=[dict(encoding="base64", compress=True)] * 5)
+    f = bad / "view_0003.vti"
+    data = f.read_bytes()
+    cut = data.index(b"_") + 40
+    f.write_bytes(data[:cut] + b"AAAA" + data[cut + 4:])
+    cmd_bad = [str(bad) if x == str(tmp_path) else x for x in cmd[:-1]] + [str(bad / "vol.mhd")]
+    r = subprocess.run(cmd_bad, capture_output=True, text=True)
+    assert r.returncode != 0
+    assert not (bad / "vol.raw").exists() and not (bad / "vol.mhd").exists()
     # coloration through the CLI
     pts = syn.fibonacci_sphere_points(2000)
     pts.tofile(str(tmp_path / "pts.f32"))

@@ -368,6 +368,18 @@ def test_error_codes(gpu_ctx):
     assert e.value.code == _lib.DMI_ERR_NO_VIEWS                # CudaReconstruction.cu:308-312
     with pytest.raises(DmiError):
         gpu_ctx.set_slab(3, 2)
+    # prepared views: the spare -1.0f slot is addressed by a 32-bit offset from every view of the call
+    import torch
+    gpu_ctx.volume_begin(None, np.float64)
+    ncls, ntile = gpu_ctx.prepared_view_sizes()
+    cls = torch.full((2 * ncls + 1,), -1.0, dtype=torch.float32, device="cuda")
+    tiles = torch.zeros(2 * ntile, dtype=torch.float32, device="cuda")
+    d = torch.zeros(2 * ncls, dtype=torch.float64, device="cuda")
+    K = np.tile(np.eye(4).reshape(1, 16), (2, 1))
+    for spare in (1 << 33, -(1 << 33)):
+        with pytest.raises(DmiError) as e:
+            gpu_ctx.volume_integrate_prepared(2, d.data_ptr(), cls.data_ptr(), spare, tiles.data_ptr(), K, K)
+        assert e.value.code == _lib.DMI_ERR_INVALID_ARGUMENT
 
 
 def test_filter_class_mirrors_reference_api(oracle):
