@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-coloration", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the B1 leg (the reference's CUDA kernel on this GPU)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the dense (--cull 0) and all-valid-depth scene lines")
     ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
     ap.add_argument("--group", type=int, default=128, help="views per all-gather group (N>1)")
     ap.add_argument("--exchange", default="ce", choices=["ce", "fused", "nccl", "nccl-split"],
@@ -68,8 +70,8 @@ def parse_args():
     ap.add_argument("--breakdown", action="store_true", help="N>1: print the comm / compute / gather spans of the last step to stderr")
     ap.add_argument("--cost-model", default="iid", choices=["iid", "coherent"],
                     help="synthetic best-cost maps: independent per pixel (default, the headline workload) or spatially coherent")
-    ap.add_argument("--color-points", type=int, default=2000000)
-    ap.add_argument("--color-views", type=int, default=200)
+    ap.add_argument("--color-points", type=int, default=10000000)
+    ap.add_argument("--color-views", type=int, default=1000)
     return ap.parse_args()
 
 
@@ -131,16 +133,27 @@ class ClockSampler:
 # reference arm: the reference's own kernel text compiled for the host (oracle/_ref), all host threads
 # ------------------------------------------------------------------------------------------------
 
+def host_threads():
+    """Host threads this process may use (its CPU affinity mask, else the core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rate(N, V, W, H, target_seconds=12.0, steps=1, warmup=0):
     """Times oracle/_ref/libref_tsdf_host.so (kind "reference") or, if absent, oracle/liboracle.so
     (kind "port") on a bounded sample of the workload: all N x N cells of `nz` z-planes in the middle
-    of the grid x `nv` views.  Returns (units/s, description dict, seconds per step)."""
+    of the grid x `nv` views.  Returns (units/s, description dict, seconds per step).
+    The OpenMP thread count is set explicitly (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)
+    and the count the library reports back is what `cores` states."""
     from cudadepthmapintegration_b200 import synthetic as syn
     from tests import _oracle
     ref = _oracle.load_ref_host()
     kind = "reference" if ref is not None else "port"
     orc = _oracle.load_oracle()
-    cores = os.cpu_count() or 1
+    orc.threads(host_threads())
+    cores = ref.threads(host_threads()) if ref is not None else orc.threads()
     grid = syn.make_grid(N)
     rp = syn.make_ray_potential(grid)
     nv = min(V, 4)
@@ -172,7 +185,8 @@ def cpu_reference_rate(N, V, W, H, target_seconds=12.0, steps=1, warmup=0):
     rate = u / (sum(times) / len(times))
     desc = {"kind": kind, "cores": cores,
             "sample": f"{nz} z-planes x {N}x{N} cells x {nv} views of {W}x{H} ({u:.3g} voxel*views per step), "
-                      f"OpenMP over (k,j) on all host threads; mean {1e3 * sum(times) / len(times):.0f} ms/step"}
+                      f"OpenMP over (k,j) on {cores} host threads (omp_get_max_threads after omp_set_num_threads); "
+                      f"mean {1e3 * sum(times) / len(times):.0f} ms/step"}
     return rate, desc, sum(times) / len(times)
 
 
@@ -210,7 +224,8 @@ def mesh_points(P):
     return np.ascontiguousarray(pts[order].astype(np.float32))
 
 
-def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
+def measure_coloration(args, ctx, torch, dev, W, H, fp64_peak, fp32_peak, steps=3, warmup=2):
+    """Secondary metric (BASELINE.json): colored points/sec at config 5's shape (~10 M points x 1000 views)."""
     from cudadepthmapintegration_b200 import synthetic as syn
     from tests import _oracle
     P, V = args.color_points, args.color_views
@@ -240,22 +255,162 @@ def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     kms, kn = ctx.color_kernel_stats()
+    ksec = kms / max(kn, 1) * 1e-3
+    tflops = COLOR_FLOPS_PER_UNIT * P * V / ksec / 1e12
+    alg_bytes = 3.0 * V * W * H + 22.0 * P                        # every colour image once + points in + results out
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     out = {"metric": "colored points/sec", "value": P / (ms * 1e-3), "unit": "points/s", "point_views_per_s": P * V / (ms * 1e-3),
-           "ms_per_step": ms, "kernel_ms_per_step": kms / max(kn, 1),
-           "config": {"workload": f"mesh coloration {P} points (sphere, scanline order, float32) x {V} views {W}x{H}"},
-           "gpu_launches_per_step": kn / max(steps, 1)}
-    # parity spot check + CPU baseline on a bounded sample (the oracle, OpenMP over points)
+           "ms_per_step": ms, "steps": steps, "warmup": warmup, "kernel_ms_per_step": kms / max(kn, 1),
+           "config": {"workload": f"mesh coloration {P} points (sphere, scanline order, float32) x {V} views {W}x{H}",
+                      "l2": "colour images (%.1f GB) exceed L2; no flush needed" % (3.0 * V * W * H / 1e9)},
+           "gpu_launches_per_step": kn / max(steps, 1),
+           "roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops / fp64_peak,
+                        "kernel": "colorize_kernel", "algorithmic_flops_per_unit": COLOR_FLOPS_PER_UNIT,
+                        "definition": "37 algorithmic FP64 flops (the reference's uncontracted projection, SURVEY.md 8d) x points x views / "
+                                      "mean CUDA-event time of the kernel launches of the timed region",
+                        "peak_source": "DFMA issue-rate microbenchmark run in this process (dmi_measure_fp_peak)",
+                        "fp32_basis": {"peak": fp32_peak, "frac": tflops / fp32_peak},
+                        "hbm": {"achieved": alg_bytes / ksec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / ksec / 1e9 / hbm_peak,
+                                "note": "algorithmic bytes (each colour image once, points, results) over kernel time; the gathers are "
+                                        "sector-granular L2 traffic, not HBM"},
+                        "ncu": ncu_summary("coloration", "colorize", 1)}}
+    # ---- end to end through dmi_colorize: pinned HOST buffers in, host arrays out, copies inside the timed region
+    import psutil
+    if 3.0 * V * W * H * 3 < 0.5 * psutil.virtual_memory().available:
+        cols_pin = torch.empty((V, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        cols_pin.copy_(cols)
+        pts_pin = torch.from_numpy(pts_h).pin_memory()
+        torch.cuda.synchronize()
+        cols_h, pts_np = cols_pin.numpy(), pts_pin.numpy()
+        ctx.colorize(pts_np[:1000], cols_h, K, RT, W, H)             # warm-up: allocates the library's device scratch
+        hmean, hmed, hnb = ctx.colorize(pts_np, cols_h, K, RT, W, H)
+        t0 = time.perf_counter()
+        hmean, hmed, hnb = ctx.colorize(pts_np, cols_h, K, RT, W, H)
+        dt = time.perf_counter() - t0
+        out["e2e"] = {"value": P / dt, "unit": "points/s", "ms_per_step": dt * 1e3, "steps": 1, "warmup": 1,
+                      "h2d_bytes_per_step": int(3 * V * W * H + pts_np.nbytes), "d2h_bytes_per_step": int(10 * P),
+                      "api": "dmi_colorize (host pointers; pinned host buffers)"}
+        same = (np.array_equal(hnb, nb.cpu().numpy()) and np.array_equal(hmed, med.cpu().numpy()) and np.array_equal(hmean, mean.cpu().numpy()))
+        out["e2e"]["equals_device_resident_result"] = bool(same)
+    else:
+        cols_h = cols.cpu().numpy()
+        out["e2e"] = {"value": None, "skipped": "not enough host memory for pinned colour images"}
+    # ---- parity spot check + CPU baselines on bounded samples
     orc = _oracle.load_oracle()
-    ns = min(P, 20000)
-    cols_h = cols.cpu().numpy()
+    used = orc.threads(host_threads())
+    ns = min(P, 100000)
+    sel = np.linspace(0, P - 1, ns).astype(np.int64)                 # spread over the whole mesh
     t0 = time.perf_counter()
-    wmean, wmed, wnb = orc.colorize(pts_h[:ns], cols_h, K, RT, W, H)
+    wmean, wmed, wnb = orc.colorize(pts_h[sel], cols_h, K, RT, W, H)
     dt = time.perf_counter() - t0
-    ok = (np.array_equal(nb[:ns].cpu().numpy(), wnb) and np.array_equal(med[:ns].cpu().numpy(), wmed)
-          and np.array_equal(mean[:ns].cpu().numpy(), wmean))
+    dsel = torch.from_numpy(sel).to(dev)
+    ok = (np.array_equal(nb[dsel].cpu().numpy(), wnb) and np.array_equal(med[dsel].cpu().numpy(), wmed)
+          and np.array_equal(mean[dsel].cpu().numpy(), wmean))
     out["parity_sample_ok"] = bool(ok)
-    out["cpu_baseline"] = {"value": ns / dt, "unit": "points/s", "cores": os.cpu_count() or 1, "kind": "port",
-                           "sample": f"first {ns} points x {V} views, oracle/color_oracle.c, OpenMP over points, {dt * 1e3:.0f} ms"}
+    out["parity_sample"] = f"{ns} points spread over the mesh x {V} views, bit-exact mean / median / count against oracle/color_oracle.c"
+    out["cpu_baseline"] = {"value": ns / dt, "unit": "points/s", "cores": used, "kind": "port",
+                           "sample": f"{ns} points x {V} views, oracle/color_oracle.c, OpenMP over points on {used} threads, {dt * 1e3:.0f} ms"}
+    refc = _oracle.load_ref_coloration()
+    if refc is not None:
+        nr, vr = min(P, 20000), min(V, 100)
+        sel2 = np.linspace(0, P - 1, nr).astype(np.int64)
+        t0 = time.perf_counter()
+        rmean, rmed, rnb = refc.colorize(pts_h[sel2], cols_h[:vr], K[:vr], RT[:vr], W, H)
+        dt2 = time.perf_counter() - t0
+        omean, omed, onb = orc.colorize(pts_h[sel2], cols_h[:vr], K[:vr], RT[:vr], W, H)
+        out["cpu_reference"] = {"value": nr * vr / dt2, "unit": "point*views/s", "cores": 1, "kind": "reference",
+                                "sample": f"{nr} points x {vr} views through the reference's own MeshColoration.cxx (single thread, VTK stand-in; "
+                                          f"includes its constructor's per-view reads), {dt2 * 1e3:.0f} ms",
+                                "equals_oracle": bool(np.array_equal(rnb, onb) and np.array_equal(rmed, omed) and np.array_equal(rmean, omean))}
+    return out
+
+
+def measure_reference_cuda(torch, dev, grid, rp, N, V, W, H, K, RT, my_depths, my_cost, host_bufs, ours, units):
+    """B1: depthMapKernel<double> of Reconstruction/CudaReconstruction.cu:47-212, compiled
+    unmodified for sm_100a (oracle/_ref/libref_tsdf_cuda*.so), driven like ProcessDepthMap's loop (:343-365: per view
+    cudaDeviceSynchronize + 3 H2D copies + one launch) on the same workload, one step.  Also the full-size parity
+    check of our volume (`ours`, device tensor) against the -fmad=false build (= the shipped -G numerics)."""
+    from tests import _oracle
+    if N > 1024:
+        return {"unavailable": "the reference's launch shape caps the grid at 1024 voxels in x (CudaReconstruction.cu:330)"}
+    if host_bufs is None:
+        return {"unavailable": "no host buffers (the end-to-end leg was skipped)"}
+    ref_o3, ref_nofma = _oracle.load_ref_cuda(nofma=False), _oracle.load_ref_cuda(nofma=True)
+    if ref_o3 is None or ref_nofma is None:
+        return {"unavailable": "oracle/_ref/libref_tsdf_cuda*.so not present (built where /root/reference exists)"}
+    h_depths, h_vol = host_bufs["depths"], host_bufs["vol"]
+    # ReconstructionData::ApplyDepthThresholdFilter runs on the host before the copy (:348): the harness gets filtered maps
+    for v0 in range(0, V, 32):
+        d, c = my_depths[v0:v0 + 32], my_cost[v0:v0 + 32]
+        h_depths[v0:v0 + 32].copy_(torch.where(c > THRESH, torch.full_like(d, -1.0), d))
+    torch.cuda.synchronize()
+    out = {"kernel": "depthMapKernel<double> (reference text, nvcc -O3 -gencode arch=compute_100a,code=sm_100a)",
+           "driven": "like ProcessDepthMap :343-365: per view cudaDeviceSynchronize + H2D of the depth map (pinned host buffer here; "
+                     "the reference's is pageable) and of K, RT + one launch; best-cost filter applied beforehand (not timed)",
+           "steps": 1, "n_gpus": 1}
+    h_vol.zero_()
+    _, kernel_ms, span_ms = ref_o3.run(grid, rp, W, H, h_depths.numpy(), K, RT, h_vol.numpy(), per_kernel_events=True)
+    out["kernel_only"] = {"value": units / (kernel_ms * 1e-3), "unit": "voxel*views/s", "ms_per_step": kernel_ms,
+                          "what": "sum of the CUDA-event times of the V launches"}
+    out["as_driven"] = {"value": units / (span_ms * 1e-3), "unit": "voxel*views/s", "ms_per_step": span_ms,
+                        "what": "first H2D to last kernel completion (volume upload / download not included)"}
+    h_vol.zero_()
+    ref_nofma.run(grid, rp, W, H, h_depths.numpy(), K, RT, h_vol.numpy(), per_kernel_events=False)
+    n_bad = n_support = 0
+    max_abs = 0.0
+    step = 1 << 26
+    for o in range(0, ours.numel(), step):
+        r = h_vol[o:o + step].to(dev, non_blocking=True)
+        g = ours[o:o + step]
+        err = (g - r).abs()
+        n_bad += int((err > 1e-6 + 1e-5 * r.abs()).sum().item())
+        n_support += int(((g != 0) != (r != 0)).sum().item())
+        max_abs = max(max_abs, float(err.max().item()))
+    out["parity_full_size"] = {"against": "the same kernel text built with -fmad=false (numerics of the shipped -G build)",
+                               "voxels": int(ours.numel()), "out_of_tolerance": n_bad, "support_mismatches": n_support,
+                               "max_abs_err": max_abs, "tolerance": "1e-6 abs + 1e-5 rel"}
+    return out
+
+
+def measure_variants(args, ctx, _lib, torch, dev, syn, grid, N, V, W, H, my_depths, my_cost, scene, step_device, timed, units):
+    """The integration kernel on inputs other than the headline's: (1) the same scene with the brick culling off (every
+    voxel*view pair evaluated one by one: the dense worst case), (2) a scene in which EVERY pixel of every depth map is
+    valid (the sphere seen from inside, cameras at radius 0.3, no best-cost maps).  2 steps each after 1 warm-up."""
+    out = {}
+
+    def run(label, note):
+        step_device()
+        ctx.tsdf_kernel_stats()
+        ms, _ = timed(step_device, 2)
+        kms, kn = ctx.tsdf_kernel_stats()
+        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 1)
+        step_device()
+        torch.cuda.synchronize()
+        t = ctx.tsdf_tier_counters()
+        ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 0)
+        out[label] = {"value": units / (ms * 1e-3), "unit": "voxel*views/s", "ms_per_step": ms, "steps": 2, "warmup": 1,
+                      "kernel_ms_per_step": kms / 2, "evaluated_fraction_of_pairs": t["units"] / units,
+                      "free_space_fraction_of_pairs": t["uniform_front"] / units,
+                      "evaluated_pairs_per_s": t["units"] / (kms / 2 * 1e-3), "what": note}
+
+    if args.cull:
+        ctx.set_option(_lib.DMI_OPT_CULL, 0)
+        run("dense_no_culling", "headline scene, DMI_OPT_CULL = 0: all N^3*V pairs evaluated voxel by voxel")
+        ctx.set_option(_lib.DMI_OPT_CULL, 1)
+    K2, RT2 = syn.make_cameras(V, W, H, radius=0.3)
+    noise = 0.25 * float(grid.spacing.max())
+    for v0 in range(0, V, 8):
+        d, _, _ = syn.render_views(K2[v0:v0 + 8], RT2[v0:v0 + 8], W, H, first_view=v0, device=dev, depth_noise=noise,
+                                   want_color=False, want_best_cost=False, scene="room")
+        my_depths[v0:v0 + 8] = d
+    torch.cuda.synchronize()
+    scene.update(K=K2, RT=RT2, use_cost=False)
+    run("all_valid_depth_room", "sphere seen from inside (cameras at radius 0.3 looking through the centre), every pixel valid, no best-cost maps")
     return out
 
 
@@ -263,14 +418,18 @@ def measure_coloration(args, ctx, torch, dev, W, H, steps, warmup):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
-# (workload, kernel, n_gpus) -> DRAM bytes per launch measured by ncu (mean of the two captured launches)
-NCU_DRAM_BYTES_PER_LAUNCH = {("config5", "auto", 1): 8.86e9}
-# same capture: the resource that actually binds the integration kernel is instruction issue
-NCU_ISSUE = {("config5", "auto", 1): {"issue_slots_busy": 0.651, "warps_eligible_per_cycle": 1.36, "fp64_pipe": 0.065, "fma_pipe": 0.243,
-                                       "alu_pipe": 0.490, "xu_pipe": 0.140, "lsu_pipe": 0.120, "l1_hit": 0.70, "l2_hit": 0.76,
-                                       "source": "ncu --set full, profiles/r1_tsdf_fast_config5_ncu_full.txt (smsp__issue_active, "
-                                                 "sm__inst_executed_pipe_*, fractions of peak); captured one kernel generation "
-                                                 "before the final one (238.6 ms per step)"}}
+def ncu_summary(workload, kernel, world):
+    """dram bytes per launch / issue statistics of the dominant kernel from the committed ncu summary
+    (profiles/ncu_summary.json: written by profiles/ncu_summary.py from an `ncu --set full` capture of this same
+    bench command; it names the commit and the kernel time of the capture).  None when there is no capture for
+    this workload -- nothing is pasted into this file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            return json.load(f).get(f"{workload}/{kernel}/n{world}")
+    except Exception:
+        return None
+
+
 EXCHANGE_TEXT = {"nccl-split": "owner-side preparation + NCCL all-gathers of the prepared arrays",
                  "fused": "prepared by their owner straight into every rank's buffers: stores over NVLink from the preparation kernel",
                  "ce": "copy-engine pushes over CUDA IPC", "nccl": "NCCL all-gather"}
@@ -437,12 +596,15 @@ def main():
 
     h2d_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
+    scene = {"K": K, "RT": RT, "use_cost": True}      # N=1 variants swap the cameras / drop the best-cost maps
+
     def step_device(host=None):
         """One full job with inputs resident in HBM (host = (depths, cost) pinned tensors: end-to-end variant,
         each group's share is uploaded on its own stream while the previous groups are integrated)."""
         ctx.volume_begin(None, np.float64)
         if world == 1:
-            ctx.volume_integrate_device(V, my_depths.data_ptr(), my_cost.data_ptr(), THRESH, K, RT)
+            ctx.volume_integrate_device(V, my_depths.data_ptr(), my_cost.data_ptr() if scene["use_cost"] else None, THRESH,
+                                        scene["K"], scene["RT"])
             return
         cur = torch.cuda.current_stream()
         comm_stream.wait_stream(cur)
@@ -629,14 +791,29 @@ def main():
         ctx.set_option(_lib.DMI_OPT_TIER_COUNTERS, 0)
 
     # ---- end to end from host buffers
-    e2e = None
+    e2e, host_bufs = None, None
     if not args.no_e2e:
-        e2e = measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units,
-                          step_device, slab_tensor, timed)
+        e2e, host_bufs = measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units,
+                                     step_device, slab_tensor, timed)
+
+    # ---- B1: the reference's own CUDA kernel on this GPU, driven like ProcessDepthMap (N=1 only: it has no multi-GPU path)
+    reference_cuda = None
+    if world == 1 and not args.no_reference_cuda and not args.emulate_rank and args.kernel != "exact":
+        step_device()
+        torch.cuda.synchronize()
+        reference_cuda = measure_reference_cuda(torch, dev, grid, rp, N, V, W, H, K, RT, my_depths, my_cost, host_bufs, slab_tensor(), units)
+
+    # ---- the same kernel on other inputs, so that the scene's share of the headline is visible (N=1 only)
+    variants = None
+    if world == 1 and not args.no_variants and not args.emulate_rank and args.kernel != "exact":
+        variants = measure_variants(args, ctx, _lib, torch, dev, syn, grid, N, V, W, H, my_depths, my_cost, scene, step_device, timed, units)
 
     coloration = None
     if rank == 0 and world == 1 and not args.no_coloration:
-        coloration = measure_coloration(args, ctx, torch, dev, W, H, max(1, args.steps), max(1, args.warmup))
+        del my_depths, my_cost
+        host_bufs = None
+        torch.cuda.empty_cache()
+        coloration = measure_coloration(args, ctx, torch, dev, W, H, fp64_peak, fp32_peak)
 
     if rank == 0:
         peaks = {}
@@ -655,13 +832,14 @@ def main():
             evaluated = tiers["units"] / (units / world)          # rank 0's slab
         ach = all_pairs_tflops * evaluated
         alg_bytes = algorithmic_bytes(N, V, W, H) / world * args.steps
+        ncu = ncu_summary(args.workload, args.kernel, world)
         roofline = {
             "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the integration kernel, from the committed
-            # ncu --set full capture of this workload (profiles/r1_tsdf_fast_config5_ncu_full.txt); config5 only
-            "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, args.kernel, world)),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the integration kernel: read from the committed
+            # summary of an ncu --set full capture of this command (None when this workload has none)
+            "traffic": (ncu or {}).get("dram_bytes_per_launch"),
             "traffic_unit": "bytes per launch (algorithmic: %.3g)" % (alg_bytes / max(kernel_launches, 1)),
-            "issue": NCU_ISSUE.get((args.workload, args.kernel, world)),
+            "ncu": ncu,
             "kernel": "tsdf_fast_kernel" if args.kernel != "exact" else "tsdf_exact_kernel",
             "definition": "28 algorithmic flops x the voxel*view pairs the kernel EVALUATED one by one (pairs settled by the exact "
                           "brick tests -- culled, or free space in front of the surface: one add -- are excluded) / summed CUDA-event time of the integration launches of the timed region",
@@ -698,6 +876,10 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if reference_cuda is not None:
+            line["reference_cuda"] = reference_cuda
+        if variants is not None:
+            line["variants"] = variants
         if coloration is not None:
             line["coloration"] = coloration
         if not args.no_cpu_baseline and world == 1:
@@ -719,7 +901,7 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
     need = 2 * nmine * npix * 8 + slab_cells * 8
     avail = psutil.virtual_memory().available
     if need * world > 0.7 * avail:
-        return {"value": None, "unit": "voxel*views/s", "skipped": f"host buffers need {need * world / 1e9:.0f} GB, {avail / 1e9:.0f} GB available"}
+        return {"value": None, "unit": "voxel*views/s", "skipped": f"host buffers need {need * world / 1e9:.0f} GB, {avail / 1e9:.0f} GB available"}, None
     h_depths = torch.empty((nmine, H, W), dtype=torch.float64, pin_memory=True)
     h_cost = torch.empty((nmine, H, W), dtype=torch.float64, pin_memory=True)
     h_vol = torch.zeros(slab_cells, dtype=torch.float64, pin_memory=True)
@@ -758,8 +940,9 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
         t2 = time.perf_counter()
         extra["via_process_depth_maps"] = {"host_zero_fill_ms": (t1 - t0) * 1e3, "call_ms": (t2 - t1) * 1e3,
                                            "note": "io_scalar zero-filled by the caller; the library verifies that on the host instead of uploading it"}
-    return {**extra, "value": units / sec, "unit": "voxel*views/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": 1,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(slab_cells * 8), "bytes_are": "per rank", "api": api}
+    return ({**extra, "value": units / sec, "unit": "voxel*views/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": 1,
+             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(slab_cells * 8), "bytes_are": "per rank", "api": api},
+            {"depths": h_depths, "cost": h_cost, "vol": h_vol})
 
 
 if __name__ == "__main__":

@@ -123,8 +123,11 @@ def make_cameras(n_views: int, width: int, height: int, seed: int = DEFAULT_SEED
 
 def render_views(K: np.ndarray, RT: np.ndarray, width: int, height: int, *, seed: int = DEFAULT_SEED,
                  first_view: int = 0, device="cpu", depth_noise: float = 0.0, want_color: bool = True,
-                 want_best_cost: bool = True, cost_model: str = "iid"):
+                 want_best_cost: bool = True, cost_model: str = "iid", scene: str = "sphere"):
     """Ray-cast the unit sphere for views K/RT (their global indices start at ``first_view``).
+
+    ``scene``: "sphere" = the sphere seen from outside (first intersection; rays that miss give -1), "room" = the
+    same sphere seen from INSIDE (cameras within it: the far intersection, every pixel has a depth).
 
     Returns (depths f64 [n,H,W], best_cost f64 [n,H,W] or None, colors u8 [n,H,W,3] or None),
     all with bottom-up rows.  ``cost_model``: "iid" = every pixel's best cost is an independent uniform in
@@ -155,7 +158,13 @@ def render_views(K: np.ndarray, RT: np.ndarray, width: int, height: int, *, seed
     c = (C * C).sum(dim=1).view(n, 1, 1) - 1.0
     disc = b * b - a * c
     hit = disc > 0
-    s = (-b - torch.sqrt(torch.clamp(disc, min=0.0))) / a     # camera-z of the hit (ray dir has z = 1)
+    root = torch.sqrt(torch.clamp(disc, min=0.0))
+    if scene == "sphere":
+        s = (-b - root) / a                                   # camera-z of the hit (ray dir has z = 1)
+    elif scene == "room":
+        s = (-b + root) / a                                   # the wall behind the origin, seen from inside
+    else:
+        raise ValueError("scene must be 'sphere' or 'room'")
     hit = hit & (s > 0)
     vidx = torch.arange(first_view, first_view + n, device=dev, dtype=torch.int64).view(n, 1, 1)
     pix = (vidx * (H * W) + torch.arange(H * W, device=dev, dtype=torch.int64).view(1, H, W))

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <climits>
 #include <stdlib.h>
+#include <omp.h>
 
 using std::abs;
 using std::sqrt;
@@ -50,6 +51,14 @@ static inline int ref_cuda_round_to_int(double x)
 #undef round
 
 extern "C" {
+
+// Host threads of the OpenMP loop below: n > 0 sets the count (torch.distributed.run exports OMP_NUM_THREADS=1
+// to its workers, which would silently make this a single-threaded baseline); returns the count in effect.
+int ref_host_threads(int n)
+{
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
 
 // CudaInitialize, CudaReconstruction.cu:269-298, minus the vtkMatrix4x4 unpacking.
 void ref_host_initialize(const double* gridMatrix, const int* gridDims, const double* gridOrig,

@@ -38,6 +38,15 @@
 #define ORACLE_F32 0
 #define ORACLE_F64 1
 
+/* Host threads of the OpenMP loops of the oracle (n > 0 sets the count; returns the count in effect).
+ * torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: a timed baseline must say what it used. */
+#include <omp.h>
+int oracle_threads(int n)
+{
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
+
 /* CUDA's cvt.rzi.s32.f64 (what `int = double` compiles to on the device; SASS F2I.F64.TRUNC):
  * saturating; a NaN from an .f64 source converts to 1 << 31 = INT_MIN (PTX ISA, cvt, "NaN input":
  * zero only when the source is not .f64).  Measured on B200 with the reference kernel itself

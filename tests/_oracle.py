@@ -47,6 +47,13 @@ class Oracle:
         lib.oracle_colorize.restype = None
         lib.oracle_colorize.argtypes = [_sz, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]
 
+        lib.oracle_threads.restype = C.c_int
+        lib.oracle_threads.argtypes = [_i]
+
+    def threads(self, n=0):
+        """Sets (n > 0) and returns the number of host threads the oracle's OpenMP loops use."""
+        return int(self.lib.oracle_threads(int(n)))
+
     def ray_potential(self, real, depth, thick, rho, eta, delta):
         return self.lib.oracle_ray_potential(real, depth, thick, rho, eta, delta)
 
@@ -133,6 +140,12 @@ class RefHost:
         lib.ref_host_initialize.argtypes = [_vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp]
         lib.ref_host_process.restype = None
         lib.ref_host_process.argtypes = [_i, _vp, _vp, _vp, _i, _vp, _i, _i]
+        lib.ref_host_threads.restype = C.c_int
+        lib.ref_host_threads.argtypes = [_i]
+
+    def threads(self, n=0):
+        """Sets (n > 0) and returns the number of host threads the harness' OpenMP loop uses."""
+        return int(self.lib.ref_host_threads(int(n)))
 
     def run(self, grid, rp, W, H, depths, K, RT, io_scalar, kz0=None, kz1=None):
         gm = _f64(grid.matrix); pd = np.ascontiguousarray(grid.point_dims, dtype=np.int32)

@@ -370,6 +370,7 @@ def test_error_codes(gpu_ctx):
         gpu_ctx.set_slab(3, 2)
     # prepared views: the spare -1.0f slot is addressed by a 32-bit offset from every view of the call
     import torch
+    gpu_ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_AUTO)
     gpu_ctx.volume_begin(None, np.float64)
     ncls, ntile = gpu_ctx.prepared_view_sizes()
     cls = torch.full((2 * ncls + 1,), -1.0, dtype=torch.float32, device="cuda")
