@@ -37,6 +37,10 @@
 #include <unistd.h>
 
 typedef long long vtkIdType;
+#define VTK_UNSIGNED_CHAR 3
+#define VTK_INT 6
+#define VTK_FLOAT 10
+#define VTK_DOUBLE 11
 using std::ostream;
 using std::cerr;
 using std::cout;
@@ -216,6 +220,8 @@ public:
   virtual void SetComponent(vtkIdType t, int c, double v) = 0;
   virtual vtkDataArray* NewInstance() const = 0;
   virtual void DeepCopy(const vtkDataArray* o) = 0;
+  virtual int GetDataType() const = 0;
+  virtual void* GetVoidPointer(vtkIdType id) = 0;
   void FillComponent(int c, double v) { for (vtkIdType t = 0, n = GetNumberOfTuples(); t < n; t++) SetComponent(t, c, v); }
   double GetTuple1(vtkIdType t) const { return GetComponent(t, 0); }
   void SetTuple1(vtkIdType t, double v) { SetComponent(t, 0, v); }
@@ -228,10 +234,18 @@ protected:
   double Legacy[4];
 };
 
+template <class V> struct vtkStandInTypeCode;
+template <> struct vtkStandInTypeCode<double> { enum { value = VTK_DOUBLE }; };
+template <> struct vtkStandInTypeCode<float> { enum { value = VTK_FLOAT }; };
+template <> struct vtkStandInTypeCode<unsigned char> { enum { value = VTK_UNSIGNED_CHAR }; };
+template <> struct vtkStandInTypeCode<int> { enum { value = VTK_INT }; };
+
 template <class V, class Self>
 class vtkStandInArray : public vtkDataArray
 {
 public:
+  int GetDataType() const { return vtkStandInTypeCode<V>::value; }
+  void* GetVoidPointer(vtkIdType id) { return Data.data() + id; }
   static Self* New() { return new Self; }
   static Self* SafeDownCast(vtkObjectBase* o) { return dynamic_cast<Self*>(o); }
   void SetNumberOfTuples(vtkIdType n) { Data.resize((size_t)n * NumberOfComponents); }

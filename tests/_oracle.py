@@ -238,6 +238,57 @@ class RefColoration:
         return int(out[0]), int(out[1])
 
 
+class OperatorHarness:
+    """oracle/adapter_harness.cpp: the reference's own vtkCudaReconstructionFilter / MeshColoration classes driven through
+    their public interfaces -- over adapters/*.cxx + libdmi_b200.so (libadapter_vtk.so) or over the reference's own
+    CudaReconstruction.cu / MeshColoration.cxx (libref_full.so)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.harness_filter_run.restype = C.c_int
+        lib.harness_filter_run.argtypes = [C.c_char_p, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]
+        lib.harness_coloration_run.restype = C.c_int
+        lib.harness_coloration_run.argtypes = [C.c_char_p, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]
+
+    def reconstruct(self, grid, rp, W, H, depths, best_cost, threshold, K, RT):
+        import tempfile
+        gm = _f64(grid.matrix); pd = np.ascontiguousarray(grid.point_dims, dtype=np.int32)
+        og = _f64(grid.origin); sp = _f64(grid.spacing)
+        K = _f64(K); RT = _f64(RT); depths = _f64(depths)
+        bc = None if best_cost is None else _f64(best_cost)
+        out = np.full(grid.n_voxels, np.nan)
+        sec = C.c_double(0.0)
+        with tempfile.TemporaryDirectory(prefix="dmi_harness_") as d:
+            rc = self.lib.harness_filter_run(d.encode(), _p(gm), _p(pd), _p(og), _p(sp), rp.thick, rp.rho, rp.eta, rp.delta,
+                                             float(threshold), K.size // 16, _p(depths), _p(bc), _p(K), _p(RT), W, H, _p(out),
+                                             C.addressof(sec))
+        if rc != 0:
+            raise RuntimeError(f"operator harness: filter failed ({rc})")
+        return out, sec.value
+
+    def colorize(self, xyz, colors, K, RT, W, H):
+        import tempfile
+        xyz = np.ascontiguousarray(xyz)
+        P = xyz.size // 3
+        K = _f64(K); RT = _f64(RT)
+        colors = np.ascontiguousarray(colors, dtype=np.uint8)
+        mean = np.zeros((P, 3), dtype=np.uint8); median = np.zeros((P, 3), dtype=np.uint8); nb = np.zeros(P, dtype=np.int32)
+        with tempfile.TemporaryDirectory(prefix="dmi_harness_") as d:
+            rc = self.lib.harness_coloration_run(d.encode(), P, _p(xyz), F64 if xyz.dtype == np.float64 else F32, K.size // 16,
+                                                 _p(colors), _p(K), _p(RT), W, H, _p(mean), _p(median), _p(nb))
+        if rc != 0:
+            raise RuntimeError(f"operator harness: coloration failed ({rc})")
+        return mean, median, nb
+
+
+def load_adapter_vtk():
+    return _load_ref("libadapter_vtk.so", OperatorHarness)
+
+
+def load_ref_full():
+    return _load_ref("libref_full.so", OperatorHarness)
+
+
 def load_ref_coloration():
     return _load_ref("libref_coloration.so", RefColoration)
 
