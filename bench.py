@@ -56,18 +56,10 @@ def parse_args():
     ap.add_argument("--no-reference-cuda", action="store_true", help="skip the B1 leg (the reference's CUDA kernel on this GPU)")
     ap.add_argument("--no-variants", action="store_true", help="skip the dense (--cull 0) and all-valid-depth scene lines")
     ap.add_argument("--cull", type=int, default=1, help="0: disable the brick culling of the fast kernel (dense worst case)")
-    ap.add_argument("--group", type=int, default=128, help="views per all-gather group (N>1)")
-    ap.add_argument("--exchange", default="ce", choices=["ce", "fused", "nccl", "nccl-split"],
-                    help="N>1 view exchange: 'ce' = owner-side preparation + copy-engine pushes into CUDA-IPC mapped peer buffers (no SMs; "
-                         "the fastest measured), 'fused' = the preparation kernel stores its outputs straight into every rank's mapped "
-                         "buffers over NVLink (measured slower: SM stores reach ~230 GB/s and hold SMs the integration wants), "
-                         "'nccl' = all-gather of the double maps + preparation on every rank, 'nccl-split' = owner-side preparation + "
-                         "NCCL all-gathers of the prepared arrays (not measured yet)")
     ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
-                    help="N=1 diagnostic: integrate only the z-slab that RANK of WORLD would own (value counts that slab's pairs)")
-    ap.add_argument("--quota", type=int, default=0, help="bricks per CTA of the integration kernel (0: 32 at N=1, 8 at N>1)")
-    ap.add_argument("--push-streams", type=int, default=4, help="N>1, --exchange ce: streams the peer copies are spread over")
-    ap.add_argument("--breakdown", action="store_true", help="N>1: print the comm / compute / gather spans of the last step to stderr")
+                    help="N=1 diagnostic: integrate only the z-layers that RANK of WORLD would own (value counts those pairs)")
+    ap.add_argument("--quota", type=int, default=0, help="bricks per CTA of the integration kernel (0: the library's default, 32 at N=1, 8 at N>1)")
+    ap.add_argument("--breakdown", action="store_true", help="N>1: add the per-rank compute / gather spans of the last step to the line")
     ap.add_argument("--cost-model", default="iid", choices=["iid", "coherent"],
                     help="synthetic best-cost maps: independent per pixel (default, the headline workload) or spatially coherent")
     ap.add_argument("--color-points", type=int, default=10000000)
@@ -224,40 +216,51 @@ def mesh_points(P):
     return np.ascontiguousarray(pts[order].astype(np.float32))
 
 
-def measure_coloration(args, ctx, torch, dev, W, H, fp64_peak, fp32_peak, steps=3, warmup=2):
-    """Secondary metric (BASELINE.json): colored points/sec at config 5's shape (~10 M points x 1000 views)."""
-    from cudadepthmapintegration_b200 import synthetic as syn
+def measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak, fp32_peak, timed, steps=3, warmup=2):
+    """Secondary metric (BASELINE.json): colored points/sec at config 5's shape (~10 M points x 1000 views).  N>1: points
+    sharded by contiguous index range (dmi_shard_range), every rank renders ("loads") one block of the colour images and
+    the library all-gathers them with NCCL inside the timed region (dmi_shard_colorize_device)."""
+    from cudadepthmapintegration_b200 import engine, synthetic as syn
     from tests import _oracle
     P, V = args.color_points, args.color_views
     K, RT = syn.make_cameras(V, W, H)
-    cols = torch.empty((V, H, W, 3), dtype=torch.uint8, device=dev)
-    for v0 in range(0, V, 8):
-        _, _, c = syn.render_views(K[v0:v0 + 8], RT[v0:v0 + 8], W, H, first_view=v0, device=dev, want_best_cost=False)
-        cols[v0:v0 + 8] = c
+    v0, nv = engine.shard_range(V, world, rank)
+    p0, npts = engine.shard_range(P, world, rank)
+    cols = torch.empty((max(nv, 1), H, W, 3), dtype=torch.uint8, device=dev)
+    for q in range(0, nv, 8):
+        m = min(8, nv - q)
+        _, _, c = syn.render_views(K[v0 + q:v0 + q + m], RT[v0 + q:v0 + q + m], W, H, first_view=v0 + q, device=dev, want_best_cost=False)
+        cols[q:q + m] = c
     pts_h = mesh_points(P)
-    pts = torch.from_numpy(pts_h).to(dev)
-    mean = torch.zeros((P, 3), dtype=torch.uint8, device=dev)
+    pts = torch.from_numpy(pts_h[p0:p0 + npts]).to(dev)
+    mean = torch.zeros((max(npts, 1), 3), dtype=torch.uint8, device=dev)
     med = torch.zeros_like(mean)
-    nb = torch.zeros(P, dtype=torch.int32, device=dev)
+    nb = torch.zeros(max(npts, 1), dtype=torch.int32, device=dev)
 
     def step():
-        ctx.colorize_device(P, pts.data_ptr(), np.float32, V, cols.data_ptr(), K, RT, W, H, mean.data_ptr(), med.data_ptr(), nb.data_ptr())
+        if world == 1:
+            ctx.colorize_device(P, pts.data_ptr(), np.float32, V, cols.data_ptr(), K, RT, W, H, mean.data_ptr(), med.data_ptr(), nb.data_ptr())
+        else:
+            ctx.shard_colorize_device(npts, pts.data_ptr(), np.float32, V, cols.data_ptr(), K, RT, W, H, mean.data_ptr(), med.data_ptr(),
+                                      nb.data_ptr())
 
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     ctx.color_kernel_stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    ms, _ = timed(step, steps)
     kms, kn = ctx.color_kernel_stats()
+    # order-independent digest of the three output arrays over ALL points: equal across --gpus N
+    wgt = torch.arange(p0 + 1, p0 + npts + 1, dtype=torch.int64, device=dev)
+    dig = (wgt * (nb[:npts].to(torch.int64) + 7 * mean[:npts].to(torch.int64).sum(1) + 13 * med[:npts].to(torch.int64).sum(1))).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(dig)
+    digest = "%016x" % (int(dig.item()) & 0xFFFFFFFFFFFFFFFF)
+    if rank != 0:
+        return None
     ksec = kms / max(kn, 1) * 1e-3
-    tflops = COLOR_FLOPS_PER_UNIT * P * V / ksec / 1e12
-    alg_bytes = 3.0 * V * W * H + 22.0 * P                        # SURVEY.md 8d: every colour image once + points in + results out
+    tflops = COLOR_FLOPS_PER_UNIT * npts * V / ksec / 1e12          # rank 0's kernel: its points x all views
+    alg_bytes = 3.0 * V * W * H + 22.0 * npts                       # SURVEY.md 8d: every colour image once + points in + results out
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -265,20 +268,25 @@ def measure_coloration(args, ctx, torch, dev, W, H, fp64_peak, fp32_peak, steps=
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     out = {"metric": "colored points/sec", "value": P / (ms * 1e-3), "unit": "points/s", "point_views_per_s": P * V / (ms * 1e-3),
-           "ms_per_step": ms, "steps": steps, "warmup": warmup, "kernel_ms_per_step": kms / max(kn, 1),
+           "n_gpus": world, "ms_per_step": ms, "steps": steps, "warmup": warmup, "kernel_ms_per_step": kms / max(kn, 1),
+           "result_digest": digest,
            "config": {"workload": f"mesh coloration {P} points (sphere, scanline order, float32) x {V} views {W}x{H}",
+                      "parallelism": "one GPU" if world == 1 else f"points sharded by contiguous index range over {world} GPUs; colour images "
+                                     "all-gathered with NCCL inside the timed region (dmi_shard_colorize_device)",
                       "l2": "colour images (%.1f GB) exceed L2; no flush needed" % (3.0 * V * W * H / 1e9)},
            "gpu_launches_per_step": kn / max(steps, 1),
            "roofline": {"bound": "fp64", "achieved": tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops / fp64_peak,
                         "kernel": "colorize_kernel", "algorithmic_flops_per_unit": COLOR_FLOPS_PER_UNIT,
-                        "definition": "37 algorithmic FP64 flops (the reference's uncontracted projection, SURVEY.md 8d) x points x views / "
-                                      "mean CUDA-event time of the kernel launches of the timed region",
+                        "definition": "37 algorithmic FP64 flops (the reference's uncontracted projection, SURVEY.md 8d) x rank 0's points x views / "
+                                      "mean CUDA-event time of its kernel launches of the timed region",
                         "peak_source": "DFMA issue-rate microbenchmark run in this process (dmi_measure_fp_peak)",
                         "fp32_basis": {"peak": fp32_peak, "frac": tflops / fp32_peak},
                         "hbm": {"achieved": alg_bytes / ksec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / ksec / 1e9 / hbm_peak,
                                 "note": "algorithmic bytes (each colour image once, points, results) over kernel time; the gathers are "
                                         "sector-granular L2 traffic, not HBM"},
                         "ncu": ncu_summary("coloration", "colorize", 1)}}
+    if world > 1:
+        return out
     # ---- end to end through dmi_colorize: pinned HOST buffers in, host arrays out, copies inside the timed region
     import psutil
     if 3.0 * V * W * H * 3 < 0.5 * psutil.virtual_memory().available:
@@ -430,9 +438,6 @@ def ncu_summary(workload, kernel, world):
         return None
 
 
-EXCHANGE_TEXT = {"nccl-split": "owner-side preparation + NCCL all-gathers of the prepared arrays",
-                 "fused": "prepared by their owner straight into every rank's buffers: stores over NVLink from the preparation kernel",
-                 "ce": "copy-engine pushes over CUDA IPC", "nccl": "NCCL all-gather"}
 _JSON_OUT = None
 
 
@@ -461,7 +466,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cudadepthmapintegration_b200 import Context, _lib, sharding, synthetic as syn, distributed as D
+    from cudadepthmapintegration_b200 import Context, _lib, engine, synthetic as syn
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -478,79 +483,34 @@ def main():
     grid = syn.make_grid(N)
     rp = syn.make_ray_potential(grid)
     K, RT = syn.make_cameras(V, W, H)
-    k0, k1 = sharding.slab_range(N, rank, world)
-    if args.emulate_rank and world == 1:
-        k0, k1 = sharding.slab_range(N, args.emulate_rank[0], args.emulate_rank[1])
-    slab_cells = (k1 - k0) * N * N
 
     ctx = Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_option(_lib.DMI_OPT_TSDF_KERNEL, _lib.DMI_TSDF_KERNEL_EXACT if args.kernel == "exact" else _lib.DMI_TSDF_KERNEL_AUTO)
     ctx.set_option(_lib.DMI_OPT_CULL, args.cull)
-    quota = args.quota if args.quota > 0 else (32 if world == 1 else 8)
-    ctx.set_option(_lib.DMI_OPT_BRICK_QUOTA, quota)
-    ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
-    ctx.set_slab(k0, k1)
+    nccl_version = None
+    if world > 1:
+        # the library owns the multi-GPU path (dmi_comm_* / dmi_shard_*): torch.distributed only carries the NCCL
+        # unique id to the other ranks and the barriers / max-over-ranks of the timing
+        uid = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], rank, world)
+        nccl_version = ctx.comm_info()[2]
+        ctx.shard_initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
+    else:
+        ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
+        if args.emulate_rank:
+            ctx.set_slab_layers(32, args.emulate_rank[0], args.emulate_rank[1])
+    if args.quota > 0:
+        ctx.set_option(_lib.DMI_OPT_BRICK_QUOTA, args.quota)
+    slab_cells = ctx.slab_cells
 
-    # ---- view ownership: groups of G views; inside a group rank r owns a contiguous G/world share, so
-    # that an in-place all-gather of the group's region of the resident buffer assembles it.
-    groups = D.view_groups(V, args.group if world > 1 else V, world)
-    G = max(b - a for a, b in groups)
-
-    def owned(g0, g1, r=rank):
-        return D.owned_range(g0, g1, r, world)
-
-    # ---- generate this rank's views on its GPU (stands for "loaded from the files it owns")
-    noise = 0.25 * float(grid.spacing.max())
-    all_depths, peer_ptr, own_ptr, fence = None, None, None, None
-    cls_ptr = tile_ptr = None
-    if world > 1 and args.exchange in ("ce", "fused", "nccl-split"):
-        # the resident view buffers are allocated by the library (plain cudaMalloc) so that every rank can map
-        # every other rank's buffers through CUDA IPC and PUSH its share with the copy engines over NVLink.
-        # One allocation: [residual i32 V*npix][classification f32, per group: n*npix + 4 spare][tile statistics f32];
-        # (classification, residual) is the lossless 8-byte split form of the filtered double depth, so the
-        # exchange moves 8 bytes per pixel and no rank prepares a view it does not own.
-        ncls, ntile = ctx.prepared_view_sizes()
-        cls_off, acc = {}, 0
-        for (g0, g1) in groups:
-            cls_off[g0] = acc
-            acc += ((g1 - g0) * ncls + 8 + 7) // 8 * 8      # spare slot; groups stay 32-byte aligned
-        depth_bytes = (V * npix * 4 + 255) // 256 * 256
-        cls_bytes = (acc * 4 + 255) // 256 * 256
-        own_ptr = ctx.device_malloc(depth_bytes + cls_bytes + V * ntile * 4)
-        cls_ptr, tile_ptr = own_ptr + depth_bytes, own_ptr + depth_bytes + cls_bytes
-
-        class _Buf:
-            pass
-        hb = _Buf()
-        hb.__cuda_array_interface__ = {"shape": (V, H, W), "typestr": "<i4", "data": (own_ptr, False), "version": 3}
-        all_depths = torch.as_tensor(hb, device=dev)          # the residual images, viewed as a tensor
-        handles = [None] * world
-        dist.all_gather_object(handles, ctx.ipc_get_handle(own_ptr))
-        peer_ptr = [own_ptr if r == rank else ctx.ipc_open_handle(handles[r]) for r in range(world)]
-        fence = torch.zeros(1, dtype=torch.float32, device=dev)
-
-        def _wrap(ptr, shape, typestr):
-            class _B:
-                pass
-            b = _B()
-            b.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
-            return torch.as_tensor(b, device=dev)
-        cls_t, tiles_t = {}, None
-        if args.exchange == "nccl-split":
-            cls_t = {g0: _wrap(cls_ptr + cls_off[g0] * 4, (g1 - g0, H, W), "<f4") for (g0, g1) in groups}
-            tiles_t = _wrap(tile_ptr, (V, ntile), "<f4")
-        # the spare "invalid" slot after each group's classification images is written once, locally
-        minus1 = torch.full((4,), -1.0, dtype=torch.float32, device=dev)      # (the slot right behind the group's images)
-        for (g0, g1) in groups:
-            ctx.memcpy_device_async(cls_ptr + (cls_off[g0] + (g1 - g0) * ncls) * 4, minus1.data_ptr(), 16)
-        ctx.synchronize()
-    elif world > 1:
-        all_depths = torch.empty((V, H, W), dtype=torch.float64, device=dev)
-    my_idx = np.array(D.owned_views(V, args.group if world > 1 else V, rank, world), dtype=np.int64)
+    # ---- this rank's views, generated on its GPU (stands for "loaded from the files it owns"): the library says which
+    my_idx = engine.shard_view_indices(V, world, rank).astype(np.int64) if world > 1 else np.arange(V, dtype=np.int64)
     nmine = len(my_idx)
-    my_depths = torch.empty((nmine, H, W), dtype=torch.float64, device=dev)
-    my_cost = torch.empty((nmine, H, W), dtype=torch.float64, device=dev)
+    noise = 0.25 * float(grid.spacing.max())
+    my_depths = torch.empty((max(nmine, 1), H, W), dtype=torch.float64, device=dev)
+    my_cost = torch.empty((max(nmine, 1), H, W), dtype=torch.float64, device=dev)
     for s0 in range(0, nmine, 8):
         idx = my_idx[s0:s0 + 8]
         runs = np.split(idx, np.where(np.diff(idx) != 1)[0] + 1)     # render_views hashes on first_view + offset
@@ -563,26 +523,8 @@ def main():
             off += len(r)
     torch.cuda.synchronize()
 
-    # high priority: the all-gather's few CTAs must not queue behind a million integration CTAs
-    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
     marks = {}
-    full_volume, vol_base, fence2, push_streams = None, None, None, []
-    if world > 1 and peer_ptr is not None:
-        # rank 0's full volume is mapped by every rank, which pushes its finished slab straight into place
-        vol_own = ctx.device_malloc(N ** 3 * 8) if rank == 0 else None
-        hs = [ctx.ipc_get_handle(vol_own) if rank == 0 else None]
-        dist.broadcast_object_list(hs, src=0)
-        vol_base = vol_own if rank == 0 else ctx.ipc_open_handle(hs[0])
-        if rank == 0:
-            class _Vol:
-                pass
-            hv = _Vol()
-            hv.__cuda_array_interface__ = {"shape": (N ** 3,), "typestr": "<f8", "data": (vol_own, False), "version": 3}
-            full_volume = torch.as_tensor(hv, device=dev)
-        fence2 = torch.zeros(1, dtype=torch.float32, device=dev)
-        push_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(min(args.push_streams, world - 1))]
-    elif world > 1 and rank == 0:
-        full_volume = torch.empty(N ** 3, dtype=torch.float64, device=dev)
 
     def slab_tensor():
         """The context's slab (device memory owned by libdmi_b200) as a tensor, without copying."""
@@ -594,134 +536,26 @@ def main():
         h.__cuda_array_interface__ = {"shape": (slab_cells,), "typestr": "<f8", "data": (ptr, False), "version": 3}
         return torch.as_tensor(h, device=dev)
 
-    h2d_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-
     scene = {"K": K, "RT": RT, "use_cost": True}      # N=1 variants swap the cameras / drop the best-cost maps
 
-    def step_device(host=None):
-        """One full job with inputs resident in HBM (host = (depths, cost) pinned tensors: end-to-end variant,
-        each group's share is uploaded on its own stream while the previous groups are integrated)."""
+    def step_device():
+        """One full job with this rank's views resident in its HBM: N=1 = dmi_volume_integrate_device; N>1 = the sharded
+        entry point (owner-side preparation, NCCL all-gather of the prepared views group by group behind the integration)
+        + the gather of the finished layers into rank 0's whole-grid volume."""
         ctx.volume_begin(None, np.float64)
         if world == 1:
             ctx.volume_integrate_device(V, my_depths.data_ptr(), my_cost.data_ptr() if scene["use_cost"] else None, THRESH,
                                         scene["K"], scene["RT"])
             return
         cur = torch.cuda.current_stream()
-        comm_stream.wait_stream(cur)
-        uploaded = []
-        if host is not None:
-            h2d_stream.wait_stream(cur)          # the previous step is done with my_depths / my_cost
-            o = 0
-            with torch.cuda.stream(h2d_stream):
-                for (g0, g1) in groups:
-                    a, b, _ = owned(g0, g1)
-                    if b > a:
-                        my_depths[o:o + b - a].copy_(host[0][o:o + b - a], non_blocking=True)
-                        my_cost[o:o + b - a].copy_(host[1][o:o + b - a], non_blocking=True)
-                        o += b - a
-                    ev = torch.cuda.Event()
-                    ev.record(h2d_stream)
-                    uploaded.append(ev)
         if args.breakdown:
-            for nm in ("t0", "comm_done", "compute_done", "gather_done"):
+            for nm in ("t0", "compute_done", "gather_done"):
                 marks[nm] = torch.cuda.Event(enable_timing=True)
             marks["t0"].record(cur)
-        events = []
-        off = 0
-        # filter own views into place, all-gather group by group on the comm stream, integrate behind it
-        with torch.cuda.stream(comm_stream):
-            if peer_ptr is not None:
-                dist.all_reduce(fence)          # every rank is done reading the previous step's views
-            for gi, (g0, g1) in enumerate(groups):
-                a, b, per = owned(g0, g1)
-                n = b - a
-                if uploaded:
-                    comm_stream.wait_event(uploaded[gi])
-                if peer_ptr is None:
-                    if n > 0:
-                        all_depths[a:b].copy_(my_depths[off:off + n])
-                        ctx.set_stream(comm_stream.cuda_stream)
-                        ctx.apply_depth_threshold_device(n * npix, all_depths[a:b].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH)
-                        ctx.set_stream(cur.cuda_stream)
-                        off += n
-                    D.all_gather_group(dist, all_depths, g0, g1, rank, world)
-                else:
-                    if n > 0:
-                        # the owner prepares its views ONCE (filter -> float classification image + tile pyramid)
-                        # and pushes depth, classification and pyramid to every rank, itself included
-                        ctx.set_stream(comm_stream.cuda_stream)
-                        c_rel = (cls_off[g0] + (a - g0) * ncls) * 4
-                        if args.exchange == "fused":
-                            order = [rank] + [(rank + r) % world for r in range(1, world)]      # local first
-                            ctx.prepare_views_multi(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
-                                                    [peer_ptr[q] + depth_bytes + c_rel for q in order], -1,
-                                                    [peer_ptr[q] + depth_bytes + cls_bytes + a * ntile * 4 for q in order],
-                                                    d_lo=[peer_ptr[q] + a * npix * 4 for q in order])
-                            ctx.set_stream(cur.cuda_stream)
-                            off += n
-                            dist.all_reduce(fence)
-                            ev = torch.cuda.Event()
-                            ev.record(comm_stream)
-                            events.append(ev)
-                            continue
-                        ctx.prepare_views_device(n, my_depths[off:off + n].data_ptr(), my_cost[off:off + n].data_ptr(), THRESH,
-                                                 cls_ptr + c_rel, -1, tile_ptr + a * ntile * 4, d_lo=own_ptr + a * npix * 4)
-                        if args.exchange == "nccl-split":
-                            ctx.set_stream(cur.cuda_stream)
-                            off += n
-                        prepared = torch.cuda.Event()
-                        prepared.record(comm_stream)
-                        for r in range(1, world if args.exchange == "ce" else 1):      # staggered order: every link busy, no hot receiver
-                            dst = (rank + r) % world
-                            base = peer_ptr[dst]
-                            ps = push_streams[r % len(push_streams)]      # several copies in flight at once
-                            ps.wait_event(prepared)
-                            ctx.set_stream(ps.cuda_stream)
-                            ctx.memcpy_device_async(base + a * npix * 4, own_ptr + a * npix * 4, n * npix * 4)
-                            ctx.memcpy_device_async(base + depth_bytes + c_rel, cls_ptr + c_rel, n * ncls * 4)
-                            ctx.memcpy_device_async(base + depth_bytes + cls_bytes + a * ntile * 4, tile_ptr + a * ntile * 4, n * ntile * 4)
-                        for ps in push_streams:
-                            pushed = torch.cuda.Event()
-                            pushed.record(ps)
-                            comm_stream.wait_event(pushed)
-                        if args.exchange == "ce":
-                            ctx.set_stream(cur.cuda_stream)
-                            off += n
-                    if args.exchange == "nccl-split":
-                        D.all_gather_group(dist, all_depths, g0, g1, rank, world)
-                        D.all_gather_group(dist, cls_t[g0], 0, g1 - g0, rank, world)
-                        D.all_gather_group(dist, tiles_t, g0, g1, rank, world)
-                    else:
-                        dist.all_reduce(fence)      # all shares of this group have landed everywhere
-                ev = torch.cuda.Event()
-                ev.record(comm_stream)
-                events.append(ev)
-            if args.breakdown:
-                marks["comm_done"].record(comm_stream)
-        marks["groups"] = []
-        for (g0, g1), ev in zip(groups, events):
-            cur.wait_event(ev)
-            if args.breakdown:
-                ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ga.record(cur)
-            if peer_ptr is None:
-                ctx.volume_integrate_device(g1 - g0, all_depths[g0:g1].data_ptr(), None, 0.0, K[g0:g1], RT[g0:g1])
-            else:
-                ctx.volume_integrate_prepared(g1 - g0, None, cls_ptr + cls_off[g0] * 4, (g1 - g0) * ncls,
-                                              tile_ptr + g0 * ntile * 4, K[g0:g1], RT[g0:g1], d_lo=own_ptr + g0 * npix * 4)
-            if args.breakdown:
-                gb.record(cur)
-                marks["groups"].append((ga, gb))
-        # the finished slabs are gathered once (for contouring on rank 0); slabs may differ by one plane
+        ctx.shard_integrate_device(V, my_depths.data_ptr(), my_cost.data_ptr(), THRESH, K, RT)
         if args.breakdown:
             marks["compute_done"].record(cur)
-        if vol_base is not None:
-            ptr, nbytes = ctx.volume_device_ptr()
-            if nbytes:
-                ctx.memcpy_device_async(vol_base + sharding.slab_range(N, rank, world)[0] * N * N * 8, ptr, nbytes)
-            dist.all_reduce(fence2)              # every slab has landed in rank 0's volume
-        else:
-            D.gather_slabs(dist, slab_tensor(), full_volume, N * N, N, rank, world)
+        ctx.shard_gather_volume_device(0, full_volume.data_ptr() if rank == 0 else None)
         if args.breakdown:
             marks["gather_done"].record(cur)
 
@@ -764,22 +598,26 @@ def main():
     clocks = sampler.stop() if sampler else None
     kernel_ms, kernel_launches = ctx.tsdf_kernel_stats()
     launches = ctx.launch_counter() - launches0
+    breakdown = None
     if args.breakdown and world > 1:
         t0 = marks["t0"]
-        print("rank %d breakdown of the last step (ms from its start): all-gathers done %.2f, integration done %.2f, slab gather done %.2f; integration kernels %.2f"
-              % (rank, t0.elapsed_time(marks["comm_done"]), t0.elapsed_time(marks["compute_done"]), t0.elapsed_time(marks["gather_done"]),
-                 kernel_ms / args.steps), file=sys.stderr)
-        print("rank %d per-group integration spans (start, duration ms): %s" % (rank, " ".join(
-            "(%.1f,%.1f)" % (t0.elapsed_time(ga), ga.elapsed_time(gb)) for ga, gb in marks["groups"])), file=sys.stderr)
+        mine = torch.tensor([t0.elapsed_time(marks["compute_done"]), t0.elapsed_time(marks["gather_done"]), kernel_ms / args.steps],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        breakdown = {"per_rank_ms_of_the_last_step": [{"integration_enqueued_work_done": float(x[0]), "layer_gather_done": float(x[1]),
+                                                        "integration_kernels": float(x[2])} for x in allr],
+                     "note": "ms from the start of the step on each rank's stream; integration_kernels = summed spans of the integration launches"}
     value = units / (ms_step * 1e-3)
-    # bit-pattern digest of the finished volume (untimed): equal across --gpus N when the slabs concatenate exactly
+    # bit-pattern digest of the finished volume (untimed): equal across --gpus N when the shards assemble exactly
     final = full_volume if world > 1 else slab_tensor()
     digest = None
     if rank == 0:
         bits = final.view(torch.int64)
         w = torch.arange(1, bits.numel() + 1, dtype=torch.int64, device=dev)
         digest = "%016x" % (int((bits * w).sum().item()) & 0xFFFFFFFFFFFFFFFF)
-        del w
+        del w, bits
+    final = None
 
     # ---- how much of the work the fast kernel actually evaluated (diagnostic build of the kernel, untimed)
     tiers = None
@@ -793,8 +631,7 @@ def main():
     # ---- end to end from host buffers
     e2e, host_bufs = None, None
     if not args.no_e2e:
-        e2e, host_bufs = measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units,
-                                     step_device, slab_tensor, timed)
+        e2e, host_bufs = measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units, timed)
 
     # ---- B1: the reference's own CUDA kernel on this GPU, driven like ProcessDepthMap (N=1 only: it has no multi-GPU path)
     reference_cuda = None
@@ -809,11 +646,12 @@ def main():
         variants = measure_variants(args, ctx, _lib, torch, dev, syn, grid, N, V, W, H, my_depths, my_cost, scene, step_device, timed, units)
 
     coloration = None
-    if rank == 0 and world == 1 and not args.no_coloration:
+    if not args.no_coloration and not args.emulate_rank:
         del my_depths, my_cost
         host_bufs = None
+        full_volume = None
         torch.cuda.empty_cache()
-        coloration = measure_coloration(args, ctx, torch, dev, W, H, fp64_peak, fp32_peak)
+        coloration = measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak, fp32_peak, timed)
 
     if rank == 0:
         peaks = {}
@@ -829,7 +667,7 @@ def main():
         all_pairs_tflops = FLOPS_PER_UNIT * k_units / k_sec / 1e12
         evaluated = 1.0
         if tiers and tiers["brick_views"] > 0:
-            evaluated = tiers["units"] / (units / world)          # rank 0's slab
+            evaluated = tiers["units"] / (units / world)          # rank 0's share
         ach = all_pairs_tflops * evaluated
         alg_bytes = algorithmic_bytes(N, V, W, H) / world * args.steps
         ncu = ncu_summary(args.workload, args.kernel, world)
@@ -863,17 +701,24 @@ def main():
                                  "invalid_or_rejected": tiers["invalid_or_rejected"] / u,
                                  "validity_only_phase_c": tiers["validity_only"] / u,
                                  "note": "fractions of the evaluated pairs (rank 0)"}
+        par = "one GPU"
+        if world > 1:
+            par = (f"z-layers of 32 cells dealt round-robin over {world} GPUs (dmi_shard_*); prepared views (8 B/pixel lossless split depth + "
+                   f"tile statistics) all-gathered with NCCL {nccl_version} in groups of {max(1, 128 // world) * world} views behind the integration; "
+                   "finished layers gathered into rank 0's volume with NCCL send/recv inside the timed region")
         line = {
             "metric": "voxel*view updates/sec", "value": value, "unit": "voxel*views/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"TSDF integration {N}^3 cells x {V} views {W}x{H}, best-cost threshold {THRESH}, f64 volume",
-                       "name": args.workload, "parallelism": f"z-slab x{world}" + (f", views exchanged in groups of {G} ({EXCHANGE_TEXT[args.exchange]})" if world > 1 else ""),
+                       "name": args.workload, "parallelism": par,
                        "l2": "inputs (%.1f GB per step) exceed L2; no flush needed" % (algorithmic_bytes(N, V, W, H) / 1e9),
-                       "kernel": args.kernel, "cull": args.cull, "cost_model": args.cost_model, "brick_quota": quota},
+                       "kernel": args.kernel, "cull": args.cull, "cost_model": args.cost_model},
             "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
             "volume_digest": digest,
         }
+        if breakdown is not None:
+            line["breakdown"] = breakdown
         if e2e is not None:
             line["e2e"] = e2e
         if reference_cuda is not None:
@@ -888,13 +733,15 @@ def main():
         emit(json.dumps(line))
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
-def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units,
-                step_device, slab_tensor, timed):
-    """Host buffers in, host volume out."""
+def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units, timed):
+    """Host buffers in, host volume out: N=1 through the streaming drop-in of ProcessDepthMap<double>; N>1 through
+    dmi_shard_integrate_host (each rank uploads its share of the views group by group, behind the exchange and the
+    integration of earlier groups) + dmi_volume_end (each rank reads its finished layers back)."""
     import psutil
     npix = W * H
     nmine = my_depths.shape[0]
@@ -909,9 +756,8 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
     h_cost.copy_(my_cost)
     torch.cuda.synchronize()
     steps = max(1, min(args.steps, 2))
+    vol_np, d_np, c_np = h_vol.numpy(), h_depths.numpy(), h_cost.numpy()
     if world == 1:
-        vol_np, d_np, c_np = h_vol.numpy(), h_depths.numpy(), h_cost.numpy()
-
         def step():
             # what the filter's RequestData does (vtkCudaReconstructionFilter.cxx:133-147), as DmiHostClasses.h /
             # reconstruction.py do it: the zero fill of the output happens on the device, the views stream in
@@ -920,13 +766,14 @@ def measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths
             ctx.volume_integrate_host(d_np, c_np, THRESH, K, RT)
             ctx.volume_end(vol_np)
         api = "dmi_volume_begin(NULL) + dmi_volume_integrate_host + dmi_volume_end (host pointers; pinned host buffers)"
-        h2d = int(2 * nmine * npix * 8)
     else:
         def step():
-            step_device(host=(h_depths, h_cost))
-            h_vol.copy_(slab_tensor(), non_blocking=True)
-        api = "per rank: H2D of its share of the views, owner-side preparation + exchange, integration of its z-slab, D2H of its slab"
-        h2d = int(2 * nmine * npix * 8)
+            ctx.volume_begin(None, np.float64)
+            ctx.shard_integrate_host(V, d_np, c_np, THRESH, K, RT)
+            ctx.volume_end(vol_np)
+        api = ("per rank: dmi_volume_begin(NULL) + dmi_shard_integrate_host (its share of the views from pinned host memory) + "
+               "dmi_volume_end (its z-layers to host memory)")
+    h2d = int(2 * nmine * npix * 8)
     step()
     ms, wall = timed(step, steps)
     sec = max(ms, wall) * 1e-3

@@ -27,6 +27,7 @@ DMI_OPT_VIEW_CHUNK = 2
 DMI_OPT_TIER_COUNTERS = 3
 DMI_OPT_CULL = 4
 DMI_OPT_BRICK_QUOTA = 5
+DMI_UNIQUE_ID_BYTES = 128
 
 
 class DmiError(RuntimeError):
@@ -54,6 +55,8 @@ _PROTOTYPES = {
     "dmi_set_option": (C.c_int, [_vp, _i, _ll]),
     "dmi_initialize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp]),
     "dmi_set_slab": (C.c_int, [_vp, _i, _i]),
+    "dmi_set_slab_layers": (C.c_int, [_vp, _i, _i, _i]),
+    "dmi_slab_planes": (C.c_int, [_vp, _pi]),
     "dmi_process_depth_maps": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp, _vp, _i]),
     "dmi_volume_begin": (C.c_int, [_vp, _vp, _i]),
     "dmi_volume_integrate_host": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
@@ -61,9 +64,6 @@ _PROTOTYPES = {
     "dmi_volume_end": (C.c_int, [_vp, _vp]),
     "dmi_prepared_view_sizes": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "dmi_prepare_views_device": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp, _ll, _vp]),
-    "dmi_plan_tile_grid": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "dmi_plan_slab_tile_intervals": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
-    "dmi_prepare_views_multi": (C.c_int, [_vp, _i, _vp, _vp, _d, _i, _vp, _vp, _ll, _vp]),
     "dmi_volume_integrate_prepared": (C.c_int, [_vp, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
     "dmi_volume_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "dmi_apply_depth_threshold_device": (C.c_int, [_vp, _sz, _vp, _vp, _d]),
@@ -72,14 +72,29 @@ _PROTOTYPES = {
     "dmi_colorize": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dmi_colorize_device": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "dmi_color_kernel_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_ll)]),
-    "dmi_device_malloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
-    "dmi_device_free": (C.c_int, [_vp, _vp]),
-    "dmi_ipc_get_handle": (C.c_int, [_vp, _vp, C.c_char_p]),
-    "dmi_ipc_open_handle": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
-    "dmi_ipc_close_handle": (C.c_int, [_vp, _vp]),
-    "dmi_memcpy_device_async": (C.c_int, [_vp, _vp, _vp, _sz]),
     "dmi_measure_fp_peak": (C.c_int, [_vp, _i, _d, _pd]),
     "dmi_launch_counter": (C.c_int, [_vp, C.POINTER(_ll)]),
+    "dmi_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "dmi_comm_init": (C.c_int, [_vp, C.c_char_p, _i, _i]),
+    "dmi_comm_destroy": (C.c_int, [_vp]),
+    "dmi_comm_info": (C.c_int, [_vp, _pi, _pi, _pi]),
+    "dmi_shard_initialize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp]),
+    "dmi_shard_view_count": (C.c_int, [_i, _i, _i, _pi]),
+    "dmi_shard_view_indices": (C.c_int, [_i, _i, _i, _vp]),
+    "dmi_shard_integrate_device": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
+    "dmi_shard_integrate_host": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
+    "dmi_shard_gather_volume_device": (C.c_int, [_vp, _i, _vp]),
+    "dmi_shard_range": (C.c_int, [_sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
+    "dmi_shard_colorize_device": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "dmi_group_create": (C.c_int, [_vp, _i, C.POINTER(_vp)]),
+    "dmi_group_destroy": (C.c_int, [_vp]),
+    "dmi_group_last_error": (C.c_char_p, [_vp]),
+    "dmi_group_size": (C.c_int, [_vp]),
+    "dmi_group_context": (_vp, [_vp, _i]),
+    "dmi_group_set_option": (C.c_int, [_vp, _i, _ll]),
+    "dmi_group_initialize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp]),
+    "dmi_group_process_depth_maps": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp, _vp, _i]),
+    "dmi_group_colorize": (C.c_int, [_vp, _sz, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 

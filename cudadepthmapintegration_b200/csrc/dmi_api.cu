@@ -1,8 +1,7 @@
 // C ABI of libdmi_b200.so (see include/dmi_b200.h).  Host-side orchestration only: contexts, device
 // buffers, the double-buffered host->device view pipeline, chunking of views into kernel launches.
 // Everything numeric happens in tsdf_kernels.cu / color_kernels.cu; there is no CPU fallback.
-#include "../../include/dmi_b200.h"
-#include "dmi_internal.cuh"
+#include "dmi_ctx.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -17,99 +16,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct DevBuf
-{
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t bytes)
-  {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e == cudaSuccess) cap = bytes;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct EventSpan { cudaEvent_t a, b; };
-
-struct KernelStats
-{
-  std::vector<EventSpan> pending;
-  std::vector<EventSpan> pool;
-  long long launches = 0;
-  float carry = 0.f;                   // time of spans recycled before anybody asked for the statistics
-  EventSpan open() {
-    EventSpan s;
-    if (pending.size() >= 1024)        // a caller that never reads the statistics must not accumulate events
-    {
-      s = pending.front();
-      pending.erase(pending.begin());
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) carry += ms; else cudaGetLastError();
-      return s;
-    }
-    if (!pool.empty()) { s = pool.back(); pool.pop_back(); }
-    else { cudaEventCreate(&s.a); cudaEventCreate(&s.b); }
-    return s;
-  }
-  float drain() {
-    float total = carry;
-    carry = 0.f;
-    for (auto& s : pending) { float ms = 0.f; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) total += ms; pool.push_back(s); }
-    pending.clear();
-    return total;
-  }
-  void destroy() {
-    for (auto& s : pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
-    for (auto& s : pool) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
-    pending.clear(); pool.clear();
-  }
-};
-
 }  // namespace
-
-struct dmi_ctx
-{
-  int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-  bool initialized = false;
-  dmi::GridParams g{};
-  // volume slab
-  DevBuf vol;
-  size_t vol_bytes = 0;
-  int vol_type = DMI_F64;
-  bool vol_active = false;
-  // host-view pipeline: two staging slots
-  DevBuf stage_depth[2], stage_cost[2], filtered;
-  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-  bool slot_used[2] = {false, false};
-  // coloration scratch
-  DevBuf c_xyz, c_colors, c_mats, c_mean, c_median, c_nb;
-  KernelStats tsdf_stats, color_stats;
-  long long opt_kernel = DMI_TSDF_KERNEL_AUTO, opt_chunk = 0;
-  long long total_launches = 0;
-  dmi::FastChunk fast_chunk{};
-  DevBuf counters, cls, tiles, viewscratch, maskscratch;
-  bool counters_on = false;
-  bool opt_cull = true;
-  int opt_quota = 32;
-  std::string err;
-
-  int fail(int code, const std::string& msg) { err = msg; return code; }
-  int fail_cuda(cudaError_t e, const char* what)
-  {
-    err = std::string(what) + ": " + cudaGetErrorString(e);
-    cudaGetLastError();
-    return e == cudaErrorMemoryAllocation ? DMI_ERR_OUT_OF_MEMORY : DMI_ERR_CUDA;
-  }
-};
-
-#define DMI_CK(call)                                                       \
-  do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ctx->fail_cuda(e__, #call); } while (0)
-#define DMI_REQUIRE(cond, msg)                                             \
-  do { if (!(cond)) return ctx->fail(DMI_ERR_INVALID_ARGUMENT, msg); } while (0)
 
 extern "C" {
 
@@ -182,6 +89,7 @@ int dmi_destroy(dmi_ctx* ctx)
   ctx->c_xyz.release(); ctx->c_colors.release(); ctx->c_mats.release();
   ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release();
   ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
+  dmi_host::shard_release(ctx);
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -264,6 +172,7 @@ int dmi_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims
   for (int a = 0; a < 3; a++) { g.orig[a] = gridOrig[a]; g.sp[a] = gridSpacing[a]; }
   g.Nx = gridDims[0] - 1; g.Ny = gridDims[1] - 1; g.Nz = gridDims[2] - 1;
   g.k0 = 0; g.k1 = g.Nz;
+  g.layL = 0; g.layStride = 1; g.layPhase = 0; g.nLocal = g.Nz;
   g.W = depthMapDims[0]; g.H = depthMapDims[1];
   g.thick = thick; g.rho = rho; g.eta = eta; g.delta = delta;
   g.rho_over_thick = rho / thick;
@@ -279,14 +188,46 @@ int dmi_set_slab(dmi_ctx* ctx, int k0, int k1)
   if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
   DMI_REQUIRE(0 <= k0 && k0 <= k1 && k1 <= ctx->g.Nz, "slab must satisfy 0 <= k0 <= k1 <= Nz");
   ctx->g.k0 = k0; ctx->g.k1 = k1;
+  ctx->g.layL = 0; ctx->g.layStride = 1; ctx->g.layPhase = 0; ctx->g.nLocal = k1 - k0;
   ctx->vol_active = false;
   return DMI_OK;
 }
 
-static size_t slab_cells(const dmi::GridParams& g)
+int dmi_set_slab_layers(dmi_ctx* ctx, int layerPlanes, int phase, int stride)
 {
-  return (size_t)g.Nx * g.Ny * (size_t)(g.k1 - g.k0);
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  DMI_REQUIRE(layerPlanes >= 32 && layerPlanes % 32 == 0, "layerPlanes must be a positive multiple of 32");
+  DMI_REQUIRE(stride >= 1 && phase >= 0 && phase < stride, "need 0 <= phase < stride");
+  dmi::GridParams& g = ctx->g;
+  g.k0 = 0; g.k1 = g.Nz;
+  g.layL = layerPlanes; g.layStride = stride; g.layPhase = phase;
+  long long n = 0;
+  for (long long start = (long long)phase * layerPlanes; start < g.Nz; start += (long long)stride * layerPlanes)
+    n += std::min<long long>(layerPlanes, g.Nz - start);
+  g.nLocal = (int)n;
+  ctx->vol_active = false;
+  return DMI_OK;
 }
+
+int dmi_slab_planes(dmi_ctx* ctx, int* planes)
+{
+  if (!ctx || !planes) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
+  *planes = ctx->g.nLocal;
+  return DMI_OK;
+}
+
+}  // extern "C"
+namespace dmi_host {
+void set_create_error(const std::string& msg) { g_create_error = msg; }
+size_t slab_cells(const dmi::GridParams& g)
+{
+  return (size_t)g.Nx * g.Ny * (size_t)g.nLocal;
+}
+}  // namespace dmi_host
+using dmi_host::slab_cells;
+extern "C" {
 
 // True when every BIT of the host array is zero (-0.0 is not: s + t keeps its sign when nothing is added).
 // The reference's filter zero-fills its output before the call (vtkCudaReconstructionFilter.cxx:133), so
@@ -374,7 +315,8 @@ static int volume_begin_impl(dmi_ctx* ctx, const void* h_scalar, int scalarType,
   return DMI_OK;
 }
 
-static bool fast_path_applies(const dmi_ctx* ctx)
+}  // extern "C"
+bool dmi_host::fast_path_applies(const dmi_ctx* ctx)
 {
   // The certified fast path needs the regime the reference's CLI enforces (0 < Thick, finite
   // parameters; Reconstruction/main.cxx:270-271) and pixel / voxel coordinates that floats hold
@@ -386,6 +328,8 @@ static bool fast_path_applies(const dmi_ctx* ctx)
          std::isfinite(g.delta) && g.delta >= 0 && std::isfinite(g.neg_eta_rho) && std::isfinite(g.rho) && g.W < (1 << 21) &&
          g.H < (1 << 21) && g.Nx < (1 << 23) && g.Ny < (1 << 23) && g.Nz < (1 << 23);
 }
+using dmi_host::fast_path_applies;
+extern "C" {
 
 // Exact kernel over views whose depth maps at d_depths are ALREADY filtered.
 static int integrate_exact_resident(dmi_ctx* ctx, int nViews, const double* d_depths, const double* K, const double* RT)
@@ -413,8 +357,9 @@ static int integrate_exact_resident(dmi_ctx* ctx, int nViews, const double* d_de
 
 // Fast kernel over views that are ALREADY prepared (classification images + tile pyramids, see
 // launch_prepare_views): composes the per-view rows and launches chunk by chunk.
-static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo, const float* d_cls, long long clsSpare,
-                                   const float* d_tiles, const double* K, const double* RT)
+}  // extern "C"
+int dmi_host::integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo, const float* d_cls, long long clsSpare,
+                                      const float* d_tiles, const double* K, const double* RT)
 {
   const dmi::GridParams& g = ctx->g;
   const size_t npix = (size_t)g.W * g.H;
@@ -454,6 +399,9 @@ static int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_dep
   }
   return DMI_OK;
 }
+
+using dmi_host::integrate_fast_prepared;
+extern "C" {
 
 // Fast kernel over views given as the caller's depth maps + optional best-cost maps (neither modified):
 // the filter is folded into the float classification image built by the view-preparation kernel.
@@ -559,32 +507,6 @@ int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, c
   return DMI_OK;
 }
 
-int dmi_prepare_views_multi(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
-                            double thresholdBestCost, int nDst, float* const* d_cls, int* const* d_lo,
-                            long long clsSpareIndex, float* const* d_tileStats)
-{
-  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
-  if (!ctx->initialized) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_initialize has not been called");
-  if (nViews <= 0) return ctx->fail(DMI_ERR_NO_VIEWS, "no depthMap or KRTD matrix have been loaded");
-  DMI_REQUIRE(d_depths && d_cls && d_tileStats, "null argument");
-  DMI_REQUIRE(nDst >= 1 && nDst <= dmi::kMaxPrepareDst, "nDst must be between 1 and 8");
-  dmi::PrepareDst dst = {};
-  dst.n = nDst;
-  uintptr_t bits = 0;
-  for (int r = 0; r < nDst; r++)
-  {
-    DMI_REQUIRE(d_cls[r] && d_tileStats[r] && (!d_lo || d_lo[r]), "null destination");
-    DMI_REQUIRE((reinterpret_cast<uintptr_t>(d_tileStats[r]) & 15) == 0, "d_tileStats must be 16-byte aligned");
-    dst.cls[r] = d_cls[r]; dst.lo[r] = d_lo ? d_lo[r] : nullptr; dst.tiles[r] = d_tileStats[r];
-    bits |= reinterpret_cast<uintptr_t>(dst.cls[r]) | reinterpret_cast<uintptr_t>(dst.lo[r]);
-  }
-  dst.aligned = (bits & 31) == 0;
-  DMI_CK(cudaSetDevice(ctx->device));
-  DMI_CK(dmi::launch_prepare_views(d_depths, d_bestCost, thresholdBestCost, nViews, ctx->g.W, ctx->g.H, dst, clsSpareIndex, ctx->stream));
-  ctx->total_launches += 1 + dmi::tile_pyramid_layout(ctx->g.W, ctx->g.H).nLevels;   // level 0, upper levels, flag
-  return DMI_OK;
-}
-
 int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo, const float* d_cls,
                                   long long clsSpareIndex, const float* d_tileStats, const double* K, const double* RT)
 {
@@ -603,117 +525,6 @@ int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_dept
   if (rc != DMI_OK) return rc;
   DMI_CK(cudaEventRecord(span.b, ctx->stream));
   ctx->tsdf_stats.pending.push_back(span);
-  return DMI_OK;
-}
-
-// ---- which part of a view does a z-slab need? (host only; planning of cropped view exchanges) --------------
-// The image of the slab's box under a view is the convex hull of its 8 projected corners (all in front of the
-// camera); per row of 8x8-pixel tiles the hull covers one interval of tile columns.
-
-namespace {
-
-struct P2 { double x, y; };
-
-double cross2(const P2& o, const P2& a, const P2& b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); }
-
-// Andrew's monotone chain; returns the hull counter-clockwise, without the repeated first point
-std::vector<P2> convex_hull(std::vector<P2> p)
-{
-  std::sort(p.begin(), p.end(), [](const P2& a, const P2& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
-  std::vector<P2> h(2 * p.size());
-  size_t k = 0;
-  for (size_t i = 0; i < p.size(); i++) { while (k >= 2 && cross2(h[k - 2], h[k - 1], p[i]) <= 0) k--; h[k++] = p[i]; }
-  for (size_t i = p.size() - 1, t = k + 1; i > 0; i--) { while (k >= t && cross2(h[k - 2], h[k - 1], p[i - 1]) <= 0) k--; h[k++] = p[i - 1]; }
-  h.resize(k > 1 ? k - 1 : k);
-  return h;
-}
-
-}  // namespace
-
-#define DMI_PLAN_REQUIRE(cond, msg) do { if (!(cond)) { g_create_error = msg; return DMI_ERR_INVALID_ARGUMENT; } } while (0)
-
-int dmi_plan_tile_grid(const int depthMapDims[2], int* tilesPerRow, int* tileRows)
-{
-  DMI_PLAN_REQUIRE(depthMapDims && depthMapDims[0] >= 1 && depthMapDims[1] >= 1, "depth map dims must be >= 1");
-  const dmi::TilePyramid p = dmi::tile_pyramid_layout(depthMapDims[0], depthMapDims[1]);
-  if (tilesPerRow) *tilesPerRow = p.tw;
-  if (tileRows) *tileRows = p.th;
-  return DMI_OK;
-}
-
-int dmi_plan_slab_tile_intervals(const double gridMatrix[16], const int gridDims[3], const double gridOrig[3],
-                                 const double gridSpacing[3], const int depthMapDims[2], int nViews, const double* K,
-                                 const double* RT, int k0, int k1, short* firstTile, short* lastTile)
-{
-  DMI_PLAN_REQUIRE(gridMatrix && gridDims && gridOrig && gridSpacing && depthMapDims, "null argument");
-  DMI_PLAN_REQUIRE(nViews >= 0 && K && RT && firstTile && lastTile, "null argument");
-  DMI_PLAN_REQUIRE(gridDims[0] >= 2 && gridDims[1] >= 2 && gridDims[2] >= 2, "grid point dims must be >= 2 (at least one cell)");
-  DMI_PLAN_REQUIRE(depthMapDims[0] >= 1 && depthMapDims[1] >= 1, "depth map dims must be >= 1");
-  dmi::GridParams g{};
-  memcpy(g.gm, gridMatrix, sizeof(double) * 12);
-  for (int a = 0; a < 3; a++) { g.orig[a] = gridOrig[a]; g.sp[a] = gridSpacing[a]; }
-  g.Nx = gridDims[0] - 1; g.Ny = gridDims[1] - 1; g.Nz = gridDims[2] - 1;
-  g.W = depthMapDims[0]; g.H = depthMapDims[1];
-  DMI_PLAN_REQUIRE(0 <= k0 && k0 <= k1 && k1 <= g.Nz, "slab must satisfy 0 <= k0 <= k1 <= Nz");
-  const dmi::TilePyramid lay = dmi::tile_pyramid_layout(g.W, g.H);
-  const int tw = lay.tw, th = lay.th;
-  DMI_PLAN_REQUIRE(tw < 32768, "image too wide for 16-bit tile columns");
-  const double margin = 2.0;      // pixels: rounding to the nearest pixel (0.5) + slack for the arithmetic
-  for (int v = 0; v < nViews; v++)
-  {
-    short* f = firstTile + (size_t)v * th;
-    short* l = lastTile + (size_t)v * th;
-    for (int r = 0; r < th; r++) { f[r] = 1; l[r] = 0; }                 // empty
-    if (k0 == k1) continue;
-    const double* k16 = K + 16 * (size_t)v;
-    const double* rt = RT + 16 * (size_t)v;
-    std::vector<P2> pts;
-    bool behind = false;
-    for (int c = 0; c < 8 && !behind; c++)
-    {
-      // box corners in cell-index space: voxel centres (idx + 0.5) lie inside [0, N] x [0, N] x [k0, k1]
-      const double gx = g.orig[0] + ((c & 1) ? g.Nx : 0) * g.sp[0];
-      const double gy = g.orig[1] + ((c & 2) ? g.Ny : 0) * g.sp[1];
-      const double gz = g.orig[2] + ((c & 4) ? k1 : k0) * g.sp[2];
-      double w[3], cam[3], h[3];
-      for (int a = 0; a < 3; a++) w[a] = g.gm[4 * a] * gx + g.gm[4 * a + 1] * gy + g.gm[4 * a + 2] * gz + g.gm[4 * a + 3];
-      for (int a = 0; a < 3; a++) cam[a] = rt[4 * a] * w[0] + rt[4 * a + 1] * w[1] + rt[4 * a + 2] * w[2] + rt[4 * a + 3];
-      for (int a = 0; a < 3; a++) h[a] = k16[4 * a] * cam[0] + k16[4 * a + 1] * cam[1] + k16[4 * a + 2] * cam[2] + k16[4 * a + 3];
-      if (!(h[2] > 1e-9 * (std::fabs(h[0]) + std::fabs(h[1]) + 1.0))) behind = true;      // also catches NaN
-      else pts.push_back(P2{h[0] / h[2], h[1] / h[2]});
-    }
-    if (behind)
-    {
-      // the box reaches the camera plane: its image is unbounded, every tile may be needed
-      for (int r = 0; r < th; r++) { f[r] = 0; l[r] = (short)(tw - 1); }
-      continue;
-    }
-    const std::vector<P2> hull = convex_hull(pts);
-    const size_t n = hull.size();
-    for (int r = 0; r < th; r++)
-    {
-      // storage rows 8r .. 8r+7 are image rows py = H-1-row (CudaReconstruction.cu:141-149)
-      const double ylo = (double)(g.H - 1 - std::min(8 * r + 7, g.H - 1)) - margin, yhi = (double)(g.H - 1 - 8 * r) + margin;
-      double xmin = INFINITY, xmax = -INFINITY;
-      for (size_t q = 0; q < n; q++)
-      {
-        const P2 a = hull[q], b = hull[(q + 1) % n];
-        if (a.y >= ylo && a.y <= yhi) { xmin = std::min(xmin, a.x); xmax = std::max(xmax, a.x); }
-        for (const double yl : {ylo, yhi})
-          if ((a.y - yl) * (b.y - yl) < 0)                   // the edge crosses this boundary line
-          {
-            const double x = a.x + (b.x - a.x) * (yl - a.y) / (b.y - a.y);
-            xmin = std::min(xmin, x); xmax = std::max(xmax, x);
-          }
-      }
-      if (n == 1 && hull[0].y >= ylo && hull[0].y <= yhi) { xmin = xmax = hull[0].x; }
-      if (!(xmin <= xmax)) continue;
-      xmin -= margin; xmax += margin;
-      if (xmax < 0.0 || xmin > (double)(g.W - 1)) continue;
-      const int c0 = std::max(0, (int)std::floor(xmin / 8.0)), c1 = std::min(tw - 1, (int)std::floor(xmax / 8.0));
-      if (c0 <= c1) { f[r] = (short)c0; l[r] = (short)c1; }
-    }
-  }
   return DMI_OK;
 }
 
@@ -947,62 +758,6 @@ int dmi_color_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches)
   if (ms) *ms = ctx->color_stats.drain(); else ctx->color_stats.drain();
   if (launches) *launches = ctx->color_stats.launches;
   ctx->color_stats.launches = 0;
-  return DMI_OK;
-}
-
-// ---- shared device buffers -----------------------------------------------------------------------
-
-int dmi_device_malloc(dmi_ctx* ctx, size_t bytes, void** d_ptr)
-{
-  if (!ctx || !d_ptr) return DMI_ERR_INVALID_ARGUMENT;
-  DMI_CK(cudaSetDevice(ctx->device));
-  DMI_CK(cudaMalloc(d_ptr, bytes ? bytes : 1));
-  return DMI_OK;
-}
-
-int dmi_device_free(dmi_ctx* ctx, void* d_ptr)
-{
-  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
-  DMI_CK(cudaSetDevice(ctx->device));
-  DMI_CK(cudaFree(d_ptr));
-  return DMI_OK;
-}
-
-int dmi_ipc_get_handle(dmi_ctx* ctx, void* d_ptr, unsigned char handle[64])
-{
-  if (!ctx || !d_ptr || !handle) return DMI_ERR_INVALID_ARGUMENT;
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  DMI_CK(cudaSetDevice(ctx->device));
-  cudaIpcMemHandle_t h;
-  DMI_CK(cudaIpcGetMemHandle(&h, d_ptr));
-  memcpy(handle, &h, 64);
-  return DMI_OK;
-}
-
-int dmi_ipc_open_handle(dmi_ctx* ctx, const unsigned char handle[64], void** d_ptr)
-{
-  if (!ctx || !d_ptr || !handle) return DMI_ERR_INVALID_ARGUMENT;
-  DMI_CK(cudaSetDevice(ctx->device));
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle, 64);
-  DMI_CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-  return DMI_OK;
-}
-
-int dmi_ipc_close_handle(dmi_ctx* ctx, void* d_ptr)
-{
-  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
-  DMI_CK(cudaSetDevice(ctx->device));
-  DMI_CK(cudaIpcCloseMemHandle(d_ptr));
-  return DMI_OK;
-}
-
-int dmi_memcpy_device_async(dmi_ctx* ctx, void* d_dst, const void* d_src, size_t bytes)
-{
-  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
-  DMI_REQUIRE(bytes == 0 || (d_dst && d_src), "null argument");
-  DMI_CK(cudaSetDevice(ctx->device));
-  if (bytes) DMI_CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, ctx->stream));
   return DMI_OK;
 }
 

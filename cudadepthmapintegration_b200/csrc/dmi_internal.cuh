@@ -14,12 +14,21 @@ struct GridParams
   double orig[3];       // c_gridOrig
   double sp[3];         // c_gridSpacing
   int Nx, Ny, Nz;       // CELLS of the whole grid = c_gridDims - 1
-  int k0, k1;           // z-slab owned by this context, global cell indices
+  int k0, k1;           // contiguous z-slab owned by this context, global cell indices (layL == 0)
+  // layered slab (layL > 0, a multiple of 32): the context owns the layers layPhase, layPhase + layStride, ... of layL
+  // planes each; its volume holds them packed in that order.  nLocal = planes owned (k1 - k0 for a contiguous slab).
+  int layL, layStride, layPhase, nLocal;
   int W, H;             // c_depthMapDims
   double thick, rho, eta, delta;
   double rho_over_thick;  // (rho / thick) in double, as CudaReconstruction.cu:119 evaluates it
   double neg_eta_rho;     // -eta * rho, CudaReconstruction.cu:115
 };
+
+// local plane of the slab -> global cell index k (voxel centres always use GLOBAL indices, CudaReconstruction.cu:78-83)
+__host__ __device__ inline int slab_global_k(const GridParams& g, int lp)
+{
+  return g.layL ? ((lp / g.layL) * g.layStride + g.layPhase) * g.layL + lp % g.layL : g.k0 + lp;
+}
 
 // One view, reference form: rows 0..2 of matrixTR and matrixK (CudaReconstruction.cu:172,176).
 struct ViewExact

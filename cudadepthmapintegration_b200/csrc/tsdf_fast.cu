@@ -332,7 +332,7 @@ supertile_cull_kernel(const __grid_constant__ GridParams g, const __grid_constan
   if (st < nst && v < c.n)
   {
     const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ;
-    const int i0 = (st % nsi) * FSI * FBI, j0 = ((st / nsi) % nsj) * FSJ * FBJ, k0 = g.k0 + (st / (nsi * nsj)) * FSK * FM;
+    const int i0 = (st % nsi) * FSI * FBI, j0 = ((st / nsi) % nsj) * FSJ * FBJ, k0 = slab_global_k(g, (st / (nsi * nsj)) * FSK * FM);
     const ViewFast& V = gviews[v];
     const float ei = (float)(FSI * FBI - 1), ej = (float)(FSJ * FBJ - 1), ek = (float)(FSK * FM - 1);
     const float lx = 1.001f * (fabsf(V.fnx[0]) * ei + fabsf(V.fnx[1]) * ej + fabsf(V.fnx[2]) * ek);
@@ -396,7 +396,7 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
   const int bj = ((st / nsi) % nsj) * FSJ + (rr / FSI) % FSJ;
   const int bk = (st / (nsi * nsj)) * FSK + rr / (FSI * FSJ);
   if (bi >= nbi || bj >= nbj || bk >= nbk) return;
-  const int i0 = bi * FBI, j0 = bj * FBJ, k0 = g.k0 + bk * FM;
+  const int i0 = bi * FBI, j0 = bj * FBJ, lp0 = bk * FM, k0 = slab_global_k(g, lp0);     // layers are multiples of FM planes
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int W = g.W, H = g.H;
 
@@ -465,11 +465,11 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
   const float fli = (float)li, flj = (float)lj;
   const double di = (double)i, dj = (double)j, dk0 = (double)k0;
   // voxels beyond the slab's last plane (m >= nk) are computed and discarded: no divergence in the loop
-  const int nk = min(FM, g.k1 - k0);
+  const int nk = min(FM, g.nLocal - lp0);
 
   T acc[FM];
   const size_t plane = (size_t)g.Nx * g.Ny;
-  T* p = vol + ((size_t)(k0 - g.k0) * g.Ny + j) * g.Nx + i;
+  T* p = vol + ((size_t)lp0 * g.Ny + j) * g.Nx + i;
 #pragma unroll
   for (int m = 0; m < FM; m++) acc[m] = (m < nk) ? p[m * plane] : (T)0;
 
@@ -792,7 +792,7 @@ static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& 
 
 size_t tsdf_fast_mask_bytes(const GridParams& g)
 {
-  const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
+  const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.nLocal + FM - 1) / FM;
   const size_t nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
   return nsi * nsj * nsk * 12 + 16;       // masks (2 words), the active list (1 word) per supertile + the work counters
 }
@@ -803,7 +803,7 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
                              FastCounters* d_counters, int quota, cudaStream_t s)
 {
   quota = std::max(1, quota);
-  const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.k1 - g.k0 + FM - 1) / FM;
+  const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.nLocal + FM - 1) / FM;
   if (nbi <= 0 || nbj <= 0 || nbk <= 0 || c.n <= 0) return cudaSuccess;
   const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
   const unsigned grid = nsi * nsj * nsk * (FSI * FSJ * FSK);

@@ -56,19 +56,19 @@ tsdf_exact_kernel(const __grid_constant__ GridParams g, const __grid_constant__ 
   if (!b.valid) return;
   const int i = b.bi * 32 + threadIdx.x;
   const int j = b.bj * BJ + threadIdx.y;
-  const int kb = g.k0 + b.bk * M;
+  const int lp = b.bk * M, kb = slab_global_k(g, lp);           // layers are multiples of M planes
   if (i >= g.Nx || j >= g.Ny) return;
 
   double wx[M], wy[M], wz[M];
   T acc[M];
   const size_t plane = (size_t)g.Nx * g.Ny;
-  // slab-local storage: cell (i,j,k) lives at ((k-k0)*Ny + j)*Nx + i
-  T* p = vol + ((size_t)(kb - g.k0) * g.Ny + j) * g.Nx + i;
+  // slab-local storage: cell (i,j, local plane lp) lives at (lp*Ny + j)*Nx + i
+  T* p = vol + ((size_t)lp * g.Ny + j) * g.Nx + i;
 #pragma unroll
   for (int m = 0; m < M; m++)
   {
     voxel_world(g, i, j, kb + m, wx[m], wy[m], wz[m]);
-    acc[m] = (kb + m < g.k1) ? p[m * plane] : (T)0;
+    acc[m] = (lp + m < g.nLocal) ? p[m * plane] : (T)0;
   }
   const size_t npix = (size_t)g.W * g.H;
   for (int v = 0; v < c.n; v++)
@@ -76,18 +76,18 @@ tsdf_exact_kernel(const __grid_constant__ GridParams g, const __grid_constant__ 
     const double* dv = depths + npix * v;
 #pragma unroll
     for (int m = 0; m < M; m++)
-      if (kb + m < g.k1) integrate_exact<T>(g, c.v[v], dv, wx[m], wy[m], wz[m], acc[m]);
+      if (lp + m < g.nLocal) integrate_exact<T>(g, c.v[v], dv, wx[m], wy[m], wz[m], acc[m]);
   }
 #pragma unroll
   for (int m = 0; m < M; m++)
-    if (kb + m < g.k1) p[m * plane] = acc[m];
+    if (lp + m < g.nLocal) p[m * plane] = acc[m];
 }
 
 cudaError_t launch_tsdf_exact(const GridParams& g, const ExactChunk& c, const double* d_depths,
                               void* d_vol, int scalarType, cudaStream_t s)
 {
   constexpr int M = 4;
-  const int nbi = (g.Nx + 31) / 32, nbj = (g.Ny + BJ - 1) / BJ, nbk = (g.k1 - g.k0 + M - 1) / M;
+  const int nbi = (g.Nx + 31) / 32, nbj = (g.Ny + BJ - 1) / BJ, nbk = (g.nLocal + M - 1) / M;
   if (nbi <= 0 || nbj <= 0 || nbk <= 0 || c.n <= 0) return cudaSuccess;
   const unsigned grid = brick_grid_size(nbi, nbj, nbk);
   const dim3 block(32, BJ, 1);

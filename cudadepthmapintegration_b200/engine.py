@@ -105,9 +105,67 @@ class Context:
         self._ck(self._lib.dmi_set_slab(self._h, int(k0), int(k1)))
         self._slab = (int(k0), int(k1))
 
+    def set_slab_layers(self, layer_planes: int, phase: int, stride: int):
+        """Own the z-layers phase, phase + stride, ... of `layer_planes` cells each (packed in that order)."""
+        self._ck(self._lib.dmi_set_slab_layers(self._h, int(layer_planes), int(phase), int(stride)))
+        self._slab = (0, self.slab_planes())
+
+    def slab_planes(self) -> int:
+        n = C.c_int()
+        self._ck(self._lib.dmi_slab_planes(self._h, C.byref(n)))
+        return int(n.value)
+
     @property
     def slab_cells(self) -> int:
         return self._cells[0] * self._cells[1] * (self._slab[1] - self._slab[0])
+
+    # -- sharding over several GPUs (SPMD: one context per process / GPU) ---------------------------
+    def comm_init(self, unique_id: bytes | None, rank: int, world: int):
+        """ncclCommInitRank on this context's device (collective).  unique_id: 128 bytes from comm_unique_id()."""
+        self._ck(self._lib.dmi_comm_init(self._h, unique_id, int(rank), int(world)))
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._lib.dmi_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return int(r.value), int(w.value), int(v.value)
+
+    def shard_initialize(self, grid_matrix, grid_dims, grid_orig, grid_spacing, thick, rho, eta, delta, depth_map_dims):
+        """dmi_initialize + this rank's z-layers (32 cells each, dealt round-robin)."""
+        gm = _f64(grid_matrix).reshape(16)
+        gd = np.ascontiguousarray(grid_dims, dtype=np.int32).reshape(3)
+        go = _f64(grid_orig).reshape(3)
+        gs = _f64(grid_spacing).reshape(3)
+        dd = np.ascontiguousarray(depth_map_dims, dtype=np.int32).reshape(2)
+        self._ck(self._lib.dmi_shard_initialize(self._h, _ptr(gm), _ptr(gd), _ptr(go), _ptr(gs),
+                                                float(thick), float(rho), float(eta), float(delta), _ptr(dd)))
+        self._cells = (int(gd[0]) - 1, int(gd[1]) - 1, int(gd[2]) - 1)
+        self._dd = (int(dd[0]), int(dd[1]))
+        self._slab = (0, self.slab_planes())
+
+    def shard_integrate_device(self, n_views: int, d_my_depths: int, d_my_best_cost: int | None, threshold_best_cost, K, RT):
+        """Collective.  d_my_*: THIS RANK'S views (shard_view_indices order); K, RT: all n_views views."""
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        self._ck(self._lib.dmi_shard_integrate_device(self._h, int(n_views), _ptr(int(d_my_depths)) if d_my_depths else None,
+                                                      _ptr(int(d_my_best_cost)) if d_my_best_cost else None,
+                                                      float(threshold_best_cost), _ptr(K), _ptr(RT)))
+
+    def shard_integrate_host(self, n_views: int, my_depths, my_best_cost, threshold_best_cost, K, RT):
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        self._ck(self._lib.dmi_shard_integrate_host(self._h, int(n_views), _ptr(my_depths), _ptr(my_best_cost),
+                                                    float(threshold_best_cost), _ptr(K), _ptr(RT)))
+
+    def shard_gather_volume_device(self, root: int, d_full: int | None):
+        self._ck(self._lib.dmi_shard_gather_volume_device(self._h, int(root), _ptr(int(d_full)) if d_full else None))
+
+    def shard_colorize_device(self, n_my_points: int, d_my_xyz: int, xyz_dtype, n_views: int, d_my_colors: int, K, RT,
+                              width: int, height: int, d_mean: int, d_median: int, d_nb: int):
+        """Collective.  Colours this rank's points with all views; d_my_colors = this rank's block of the colour images."""
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        self._ck(self._lib.dmi_shard_colorize_device(self._h, int(n_my_points), _ptr(int(d_my_xyz)) if d_my_xyz else None,
+                                                     scalar_code(xyz_dtype), int(n_views),
+                                                     _ptr(int(d_my_colors)) if d_my_colors else None, _ptr(K), _ptr(RT),
+                                                     int(width), int(height), _ptr(int(d_mean)) if d_mean else None,
+                                                     _ptr(int(d_median)) if d_median else None, _ptr(int(d_nb)) if d_nb else None))
 
     def process_depth_maps(self, depths, best_cost, threshold_best_cost, K, RT, io_scalar: np.ndarray):
         """ProcessDepthMap<T> (CudaReconstruction.cu:302-386) on in-memory views; accumulates onto io_scalar."""
@@ -161,17 +219,6 @@ class Context:
                                                     _ptr(int(d_best_cost)) if d_best_cost else None, float(threshold),
                                                     _ptr(int(d_cls)), _ptr(int(d_lo)) if d_lo else None,
                                                     int(cls_spare_index), _ptr(int(d_tiles))))
-
-    def prepare_views_multi(self, n_views: int, d_depths: int, d_best_cost: int | None, threshold, d_cls, cls_spare_index: int,
-                            d_tiles, d_lo=None):
-        """prepare_views_device fused with its all-gather: d_cls / d_tiles / d_lo are lists of device addresses
-        (entry 0 local, the others may be peer-mapped buffers); every output is stored to all of them."""
-        n = len(d_cls)
-        arr = lambda xs: (C.c_void_p * n)(*[int(x) for x in xs])
-        self._ck(self._lib.dmi_prepare_views_multi(self._h, int(n_views), _ptr(int(d_depths)),
-                                                   _ptr(int(d_best_cost)) if d_best_cost else None, float(threshold), n,
-                                                   arr(d_cls), arr(d_lo) if d_lo is not None else None,
-                                                   int(cls_spare_index), arr(d_tiles)))
 
     def volume_integrate_prepared(self, n_views: int, d_depths: int | None, d_cls: int, cls_spare_index: int, d_tiles: int,
                                   K, RT, d_lo: int | None = None):
@@ -244,31 +291,6 @@ class Context:
         return float(ms.value), int(n.value)
 
     # -- shared device buffers (multi-GPU view exchange over the copy engines) --------------------
-    def device_malloc(self, nbytes: int) -> int:
-        p = C.c_void_p()
-        self._ck(self._lib.dmi_device_malloc(self._h, int(nbytes), C.byref(p)))
-        return int(p.value)
-
-    def device_free(self, ptr: int):
-        self._ck(self._lib.dmi_device_free(self._h, C.c_void_p(int(ptr))))
-
-    def ipc_get_handle(self, ptr: int) -> bytes:
-        buf = C.create_string_buffer(64)
-        self._ck(self._lib.dmi_ipc_get_handle(self._h, C.c_void_p(int(ptr)), buf))
-        return buf.raw
-
-    def ipc_open_handle(self, handle: bytes) -> int:
-        p = C.c_void_p()
-        self._ck(self._lib.dmi_ipc_open_handle(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
-        return int(p.value)
-
-    def ipc_close_handle(self, ptr: int):
-        self._ck(self._lib.dmi_ipc_close_handle(self._h, C.c_void_p(int(ptr))))
-
-    def memcpy_device_async(self, dst: int, src: int, nbytes: int):
-        self._ck(self._lib.dmi_memcpy_device_async(self._h, C.c_void_p(int(dst)), C.c_void_p(int(src)), int(nbytes)))
-
-    # -- measurement -----------------------------------------------------------------------------
     def launch_counter(self) -> int:
         n = C.c_longlong()
         self._ck(self._lib.dmi_launch_counter(self._h, C.byref(n)))
@@ -280,25 +302,119 @@ class Context:
         return float(t.value)
 
 
-def plan_slab_tile_intervals(grid_matrix, point_dims, origin, spacing, depth_map_dims, K, RT, k0: int, k1: int):
-    """Which 8x8-pixel tiles (storage rows) of each view can z-slab [k0, k1) gather from?  Returns (first, last),
-    int16 [n_views, tile_rows]: the inclusive interval of tile columns per tile row, first > last = empty row.
-    Pure host planning (dmi_plan_slab_tile_intervals): needs the library, not a GPU."""
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId: call on one rank, hand the bytes to the others (e.g. torch.distributed.broadcast_object_list)."""
     lib = _lib.load()
-    gm = _f64(grid_matrix, 16)
-    pd = np.ascontiguousarray(point_dims, dtype=np.int32)
-    og, sp = _f64(origin), _f64(spacing)
-    dd = np.ascontiguousarray(depth_map_dims, dtype=np.int32)
-    K = _f64(K, 16); RT = _f64(RT, 16)
-    n = K.size // 16
-    tw, th = C.c_int(), C.c_int()
-    rc = lib.dmi_plan_tile_grid(_ptr(dd), C.byref(tw), C.byref(th))
-    if rc != 0:
-        raise DmiError(rc, (lib.dmi_last_error(None) or b"").decode())
-    first = np.empty((n, th.value), dtype=np.int16)
-    last = np.empty((n, th.value), dtype=np.int16)
-    rc = lib.dmi_plan_slab_tile_intervals(_ptr(gm), _ptr(pd), _ptr(og), _ptr(sp), _ptr(dd), n, _ptr(K), _ptr(RT), int(k0), int(k1),
-                                          _ptr(first), _ptr(last))
-    if rc != 0:
-        raise DmiError(rc, (lib.dmi_last_error(None) or b"").decode())
-    return first, last
+    buf = C.create_string_buffer(_lib.DMI_UNIQUE_ID_BYTES)
+    rc = lib.dmi_comm_unique_id(buf)
+    if rc != _lib.DMI_OK:
+        msg = lib.dmi_last_error(None)
+        raise DmiError(rc, msg.decode() if msg else "")
+    return buf.raw
+
+
+def shard_view_indices(n_views: int, world: int, rank: int) -> np.ndarray:
+    """Global indices of the views `rank` must supply to the sharded entry points, in the order expected."""
+    lib = _lib.load()
+    n = C.c_int()
+    if lib.dmi_shard_view_count(int(n_views), int(world), int(rank), C.byref(n)) != _lib.DMI_OK:
+        raise ValueError("bad arguments")
+    out = np.zeros(max(n.value, 1), dtype=np.int32)
+    if lib.dmi_shard_view_indices(int(n_views), int(world), int(rank), _ptr(out)) != _lib.DMI_OK:
+        raise ValueError("bad arguments")
+    return out[:n.value].copy()
+
+
+def shard_range(n: int, world: int, rank: int):
+    """(first, count) of the contiguous block of n items that `rank` owns (points; colour images)."""
+    lib = _lib.load()
+    a, b = C.c_size_t(), C.c_size_t()
+    if lib.dmi_shard_range(int(n), int(world), int(rank), C.byref(a), C.byref(b)) != _lib.DMI_OK:
+        raise ValueError("bad arguments")
+    return int(a.value), int(b.value)
+
+
+def layer_cell_ranges(n_cells_z: int, world: int, rank: int, layer_planes: int = 32):
+    """[(k0, k1)] global z-ranges of the layers rank owns, in the order its packed volume holds them."""
+    out, q = [], 0
+    while (q * world + rank) * layer_planes < n_cells_z:
+        k0 = (q * world + rank) * layer_planes
+        out.append((k0, min(n_cells_z, k0 + layer_planes)))
+        q += 1
+    return out
+
+
+class Group:
+    """All the GPUs of one box behind one object (single process; dmi_group_* of include/dmi_b200.h): the multi-GPU
+    counterpart of CudaInitialize / ProcessDepthMap<T> / MeshColoration::ProcessColoration."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        rc = self._lib.dmi_group_create(_ptr(devs), int(devs.size), C.byref(h))
+        if rc != _lib.DMI_OK:
+            msg = self._lib.dmi_last_error(None)
+            raise DmiError(rc, msg.decode() if msg else "")
+        self._h = h
+        self.size = int(devs.size)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dmi_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != _lib.DMI_OK:
+            msg = self._lib.dmi_group_last_error(self._h)
+            raise DmiError(rc, msg.decode() if msg else "")
+
+    def set_option(self, option: int, value: int):
+        self._ck(self._lib.dmi_group_set_option(self._h, int(option), int(value)))
+
+    def initialize(self, grid_matrix, grid_dims, grid_orig, grid_spacing, thick, rho, eta, delta, depth_map_dims):
+        gm = _f64(grid_matrix).reshape(16)
+        gd = np.ascontiguousarray(grid_dims, dtype=np.int32).reshape(3)
+        go = _f64(grid_orig).reshape(3)
+        gs = _f64(grid_spacing).reshape(3)
+        dd = np.ascontiguousarray(depth_map_dims, dtype=np.int32).reshape(2)
+        self._ck(self._lib.dmi_group_initialize(self._h, _ptr(gm), _ptr(gd), _ptr(go), _ptr(gs), float(thick), float(rho),
+                                                float(eta), float(delta), _ptr(dd)))
+        self._cells = (int(gd[0]) - 1) * (int(gd[1]) - 1) * (int(gd[2]) - 1)
+
+    def process_depth_maps(self, depths, best_cost, threshold_best_cost, K, RT, io_scalar: np.ndarray):
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        depths = _f64(depths)
+        best_cost = None if best_cost is None else _f64(best_cost)
+        if io_scalar.size != self._cells or not io_scalar.flags["C_CONTIGUOUS"]:
+            raise ValueError("io_scalar must be a C-contiguous array of the whole grid's cells")
+        self._ck(self._lib.dmi_group_process_depth_maps(self._h, K.size // 16, _ptr(depths), _ptr(best_cost),
+                                                        float(threshold_best_cost), _ptr(K), _ptr(RT), _ptr(io_scalar),
+                                                        scalar_code(io_scalar.dtype)))
+        return io_scalar
+
+    def colorize(self, xyz: np.ndarray, colors: np.ndarray, K, RT, width: int, height: int):
+        xyz = np.ascontiguousarray(xyz)
+        if xyz.dtype not in (np.float32, np.float64):
+            xyz = xyz.astype(np.float64)
+        P = xyz.size // 3
+        K = _f64(K, 16); RT = _f64(RT, 16)
+        colors = np.ascontiguousarray(colors, dtype=np.uint8)
+        mean = np.zeros((P, 3), dtype=np.uint8)
+        median = np.zeros((P, 3), dtype=np.uint8)
+        nb = np.zeros(P, dtype=np.int32)
+        self._ck(self._lib.dmi_group_colorize(self._h, P, _ptr(xyz), scalar_code(xyz.dtype), K.size // 16, _ptr(colors), _ptr(K),
+                                              _ptr(RT), int(width), int(height), _ptr(mean), _ptr(median), _ptr(nb)))
+        return mean, median, nb

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define DMI_ABI_VERSION 1
+#define DMI_ABI_VERSION 2
 
 /* status codes */
 #define DMI_OK 0
@@ -62,8 +62,9 @@ extern "C" {
 #define DMI_OPT_VIEW_CHUNK 2         /* views per launch (0 = auto) */
 #define DMI_OPT_TIER_COUNTERS 3      /* 1: count tier decisions of the fast kernel (diagnostic build of the kernel) */
 #define DMI_OPT_CULL 4               /* 1 (default): skip (brick, view) pairs that provably contribute nothing */
-#define DMI_OPT_BRICK_QUOTA 5        /* bricks a CTA of the integration kernel takes before it retires (default 32);
-                                        lower it when higher-priority work on other streams must get in quickly */
+#define DMI_OPT_BRICK_QUOTA 5        /* tuning: bricks a CTA of the persistent integration kernel takes before it retires
+                                        (default 32; the sharded entry points use 8 so that the NCCL kernels of the
+                                        view exchange find a free SM slot quickly) */
 
 typedef struct dmi_ctx dmi_ctx;
 
@@ -99,6 +100,13 @@ int dmi_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims
  * (orig + (k + 0.5) * spacing, CudaReconstruction.cu:78-83), so slabs concatenate bit-identically.
  * Default after dmi_initialize: the whole grid.  Volume pointers below then cover the slab only. */
 int dmi_set_slab(dmi_ctx* ctx, int k0, int k1);
+/* Layered sharding: this context owns the z-layers phase, phase + stride, phase + 2*stride, ... of `layerPlanes`
+ * cells each (a multiple of 32; the grid's last layer may be shorter).  Its volume holds them packed in that order:
+ * local plane lp = q * layerPlanes + r is the global plane (q * stride + phase) * layerPlanes + r.  Dealing the layers
+ * round-robin gives every GPU a share of every view's work (contiguous slabs see a view's work concentrated on
+ * few GPUs), at the price of every GPU needing every view.  dmi_slab_planes: planes owned (either kind of slab). */
+int dmi_set_slab_layers(dmi_ctx* ctx, int layerPlanes, int phase, int stride);
+int dmi_slab_planes(dmi_ctx* ctx, int* planes);
 
 /* Replaces ProcessDepthMap<T> (CudaReconstruction.cu:302-386) for views already in host memory:
  * uploads io_scalar (the call ACCUMULATES onto its content, :323-327), applies the best-cost
@@ -146,26 +154,9 @@ int dmi_prepared_view_sizes(dmi_ctx* ctx, size_t* clsFloatsPerView, size_t* tile
 int dmi_prepare_views_device(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
                              double thresholdBestCost, float* d_cls, int* d_lo, long long clsSpareIndex,
                              float* d_tileStats);
-/* dmi_prepare_views_device fused with its all-gather: every output is stored into nDst (<= 8) sets of
- * arrays; set 0 must be local to the context's device (the level passes read it back), the others may be
- * peer GPUs' buffers opened with dmi_ipc_open_handle (plain stores over NVLink).  d_lo may be NULL. */
-int dmi_prepare_views_multi(dmi_ctx* ctx, int nViews, const double* d_depths, const double* d_bestCost,
-                            double thresholdBestCost, int nDst, float* const* d_cls, int* const* d_lo,
-                            long long clsSpareIndex, float* const* d_tileStats);
 int dmi_volume_integrate_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, const int* d_lo,
                                   const float* d_cls, long long clsSpareIndex, const float* d_tileStats,
                                   const double* K, const double* RT);
-/* Planning of cropped view exchanges (pure host functions: no context, no GPU): a rank only needs the part of a
- * view that the box of its z-slab projects onto.  Grid and image arguments as in dmi_initialize.  Tiles are 8 x 8
- * pixels of STORAGE rows (bottom-up images); the grid has tilesPerRow x tileRows tiles.  For slab [k0, k1) and each
- * view, firstTile / lastTile [nViews][tileRows] receive the inclusive interval of tile columns of every tile row
- * that some voxel centre of the slab can round into (2-pixel margin); firstTile > lastTile marks an empty row.  A
- * view whose camera plane cuts the box gets every tile.  Errors: dmi_last_error(NULL). */
-int dmi_plan_tile_grid(const int depthMapDims[2], int* tilesPerRow, int* tileRows);
-int dmi_plan_slab_tile_intervals(const double gridMatrix[16], const int gridDims[3], const double gridOrig[3],
-                                 const double gridSpacing[3], const int depthMapDims[2], int nViews, const double* K,
-                                 const double* RT, int k0, int k1, short* firstTile, short* lastTile);
-
 /* Device address and size in bytes of the slab (valid between begin and the next begin/destroy). */
 int dmi_volume_device_ptr(dmi_ctx* ctx, void** d_ptr, size_t* bytes);
 
@@ -209,22 +200,74 @@ int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyz
                         uint8_t* d_mean, uint8_t* d_median, int32_t* d_nbProjected);
 int dmi_color_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
 
-/* ---- device buffers shared between the per-GPU processes (multi-GPU view exchange) --------------- */
+/* ---- sharding over several GPUs (new; the reference is single-GPU) ---------------------------------
+ *
+ * The grid is cut into z-layers of 32 cells dealt round-robin to the GPUs (dmi_set_slab_layers): every voxel has one
+ * owner, so there is no reduction; every GPU needs every view, so the views' PREPARED form (classification float +
+ * int32 residual = the lossless 8-byte split of the filtered double depth, + tile statistics; built once, by the rank
+ * that loaded the view) is all-gathered with NCCL in groups of views, behind the integration of the previous group.
+ * Results are bit-identical to the single-GPU volume.
+ *
+ * SPMD form -- one process (or thread) per GPU, each with its own context:
+ *   dmi_comm_unique_id        ncclGetUniqueId on one rank; hand the 128 bytes to the others by any means
+ *   dmi_comm_init             ncclCommInitRank on the context's device (collective: every rank calls it)
+ *   dmi_shard_initialize      dmi_initialize + this rank's layers
+ *   dmi_shard_view_count /    which views this rank must supply ("the files it loads"), in the order expected:
+ *   dmi_shard_view_indices    groups of 128 consecutive views, each split evenly over the ranks
+ *   dmi_volume_begin          as usual, on the rank's layers (packed)
+ *   dmi_shard_integrate_*     collective; myDepths / myBestCost hold THIS RANK'S views only, K / RT all views
+ *   dmi_shard_gather_volume_device   collective; root receives the whole grid in VTK cell order (device memory)
+ *   dmi_volume_end            as usual: the rank's layers to host memory
+ *   dmi_shard_range           contiguous split of n items (coloration: points; colour images)
+ *   dmi_shard_colorize_device collective; colours THIS RANK'S points (dmi_shard_range) with all views, of which it
+ *                             supplies its own block (dmi_shard_range of the views); the blocks are all-gathered
+ * NCCL is loaded with dlopen("libnccl.so.2") at first use: a process that already holds one (PyTorch) shares it. */
+#define DMI_UNIQUE_ID_BYTES 128
+int dmi_comm_unique_id(unsigned char id[DMI_UNIQUE_ID_BYTES]);
+int dmi_comm_init(dmi_ctx* ctx, const unsigned char id[DMI_UNIQUE_ID_BYTES], int rank, int world);
+int dmi_comm_destroy(dmi_ctx* ctx);
+int dmi_comm_info(dmi_ctx* ctx, int* rank, int* world, int* ncclVersion);
+int dmi_shard_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims[3],
+                         const double gridOrig[3], const double gridSpacing[3],
+                         double rayPotentialThick, double rayPotentialRho, double rayPotentialEta,
+                         double rayPotentialDelta, const int depthMapDims[2]);
+int dmi_shard_view_count(int nViews, int world, int rank, int* count);
+int dmi_shard_view_indices(int nViews, int world, int rank, int* indices);
+int dmi_shard_integrate_device(dmi_ctx* ctx, int nViews, const double* d_myDepths, const double* d_myBestCost,
+                               double thresholdBestCost, const double* K, const double* RT);
+int dmi_shard_integrate_host(dmi_ctx* ctx, int nViews, const double* myDepths, const double* myBestCost,
+                             double thresholdBestCost, const double* K, const double* RT);
+int dmi_shard_gather_volume_device(dmi_ctx* ctx, int root, void* d_full);
+int dmi_shard_range(size_t n, int world, int rank, size_t* first, size_t* count);
+int dmi_shard_colorize_device(dmi_ctx* ctx, size_t nMyPoints, const void* d_myXyz, int xyzType, int nViews,
+                              const uint8_t* d_myColors, const double* K, const double* RT, int W, int H,
+                              uint8_t* d_mean, uint8_t* d_median, int32_t* d_nbProjected);
 
-/* Plain cudaMalloc / cudaFree on the context's device: buffers allocated here can be exported to the
- * other ranks' processes with CUDA IPC, so that the view all-gather can run on the COPY ENGINES over
- * NVLink (dmi_memcpy_device_async into a peer's mapped buffer) instead of on SMs that the integration
- * kernel needs. */
-int dmi_device_malloc(dmi_ctx* ctx, size_t bytes, void** d_ptr);
-int dmi_device_free(dmi_ctx* ctx, void* d_ptr);
-/* 64-byte cudaIpcMemHandle_t of a dmi_device_malloc buffer / mapping of a peer's handle (peer access is
- * enabled lazily) / unmapping. */
-int dmi_ipc_get_handle(dmi_ctx* ctx, void* d_ptr, unsigned char handle[64]);
-int dmi_ipc_open_handle(dmi_ctx* ctx, const unsigned char handle[64], void** d_ptr);
-int dmi_ipc_close_handle(dmi_ctx* ctx, void* d_ptr);
-/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on the context's stream; either side may be a
- * mapped peer buffer. */
-int dmi_memcpy_device_async(dmi_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+/* Single-process form: one object drives all the GPUs listed (one host thread per GPU inside each call, NCCL
+ * communicators from ncclCommInitAll).  This is the multi-GPU counterpart of the reference's two entry points:
+ *   dmi_group_initialize          CudaInitialize (CudaReconstruction.cu:269-298)
+ *   dmi_group_process_depth_maps  ProcessDepthMap<T> (:302-386): host pointers, ALL views, io_scalar = the whole grid
+ *                                 (accumulated onto); each GPU uploads only the views and the layers it owns and
+ *                                 writes its finished layers straight into io_scalar
+ *   dmi_group_colorize            MeshColoration::ProcessColoration (MeshColoration.cxx:98-199): points sharded by
+ *                                 contiguous index range; host pointers as in dmi_colorize                          */
+typedef struct dmi_group dmi_group;
+int dmi_group_create(const int* devices, int nDevices, dmi_group** grp);
+int dmi_group_destroy(dmi_group* grp);
+const char* dmi_group_last_error(const dmi_group* grp);
+int dmi_group_size(const dmi_group* grp);
+dmi_ctx* dmi_group_context(dmi_group* grp, int rank);
+int dmi_group_set_option(dmi_group* grp, int option, long long value);
+int dmi_group_initialize(dmi_group* grp, const double gridMatrix[16], const int gridDims[3],
+                         const double gridOrig[3], const double gridSpacing[3],
+                         double rayPotentialThick, double rayPotentialRho, double rayPotentialEta,
+                         double rayPotentialDelta, const int depthMapDims[2]);
+int dmi_group_process_depth_maps(dmi_group* grp, int nViews, const double* depths, const double* bestCost,
+                                 double thresholdBestCost, const double* K, const double* RT,
+                                 void* io_scalar, int scalarType);
+int dmi_group_colorize(dmi_group* grp, size_t nPoints, const void* xyz, int xyzType, int nViews,
+                       const uint8_t* colors, const double* K, const double* RT, int W, int H,
+                       uint8_t* mean, uint8_t* median, int32_t* nbProjected);
 
 /* ---- measurement helpers ------------------------------------------------------------------- */
 

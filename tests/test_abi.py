@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"libdmi_b200.so does not export {s}"
     assert sorted(_lib.exported_symbols()) == declared_symbols()
-    assert lib.dmi_abi_version() == 1
+    assert lib.dmi_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -1,7 +1,8 @@
-"""N>1 host logic on CPU: world_size-2 gloo run of the view exchange + z-slab sharding + slab gather
-(cudadepthmapintegration_b200/distributed.py, sharding.py).  The per-rank integrator here is the ORACLE
-(this is a test of the plumbing, not of the kernel): the gathered volume must be bit-identical to the
-single-process result."""
+"""N>1 host logic on CPU: a world_size-2 gloo run of the sharded job's LAYOUT -- which rank supplies which views
+(dmi_shard_view_indices), in which order a group is assembled (one in-place all-gather per group), which z-layers a
+rank owns (dmi_set_slab_layers / engine.layer_cell_ranges) and where they land in the gathered volume.  The per-rank
+integrator here is the ORACLE and the transport is gloo (this is a test of the plumbing the library implements with
+NCCL in csrc/dmi_shard.cu, not of the kernel): the assembled volume must be bit-identical to the single-process one."""
 import os
 import socket
 import sys
@@ -25,8 +26,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, group, out_path):
-    from cudadepthmapintegration_b200 import distributed as D, sharding
+def _worker(rank, world, port, n_views, out_path):
+    from cudadepthmapintegration_b200 import engine
     from tests import _oracle
     from tests.scenes import Scene
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -34,45 +35,63 @@ def _worker(rank, world, port, group, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         orc = _oracle.load_oracle()
-        s = Scene((18, 11, 7), 7, 48, 36, rotate_deg=30.0)         # 7 views: ragged last group
+        s = Scene((18, 11, 70), n_views, 48, 36, rotate_deg=30.0)       # 70 planes: layers 0..2, the last one 6 planes thick
         V = s.n_views
         nz = s.grid.n_cells[2]
         plane = s.grid.n_cells[0] * s.grid.n_cells[1]
-        # each rank "loads" and filters only the views it owns
-        mine = D.owned_views(V, group, rank, world)
-        all_views = torch.full((V, s.H, s.W), float("nan"), dtype=torch.float64)
-        for v in mine:
-            all_views[v] = torch.from_numpy(orc.apply_depth_threshold(s.depths[v], s.best_cost[v], 0.14).reshape(s.H, s.W))
-        k0, k1 = sharding.slab_range(nz, rank, world)
+        per = max(1, 128 // world)
+        G = per * world
+        # each rank "loads" and filters only the views the library says it owns, in that order
+        mine = engine.shard_view_indices(V, world, rank)
+        my_views = [torch.from_numpy(orc.apply_depth_threshold(s.depths[v], s.best_cost[v], 0.14).reshape(s.H, s.W)) for v in mine]
+        layers = engine.layer_cell_ranges(nz, world, rank)
         vol = np.zeros(s.grid.n_voxels)
-        for g0, g1 in D.view_groups(V, group, world):
-            D.all_gather_group(dist, all_views, g0, g1, rank, world)
-            assert not torch.isnan(all_views[g0:g1]).any()
-            orc.tsdf_integrate(s.grid, s.rp, s.W, s.H, all_views[g0:g1].numpy(), None, 0.0, s.K[g0:g1], s.RT[g0:g1], vol, k0, k1)
-        slab = torch.from_numpy(vol[k0 * plane:k1 * plane].copy())
-        full = torch.zeros(s.grid.n_voxels, dtype=torch.float64) if rank == 0 else None
-        D.gather_slabs(dist, slab, full, plane, nz, rank, world)
+        used = 0
+        for g0 in range(0, V, G):
+            g1 = min(V, g0 + G)
+            pg = per if g1 - g0 == G else -(-(g1 - g0) // world)
+            # the group buffer holds world * pg views; rank r's segment starts r * pg views in (padding at the end of a short group)
+            a = min(g1, g0 + rank * pg)
+            b = min(g1, a + pg)
+            seg = torch.full((pg, s.H, s.W), float("nan"), dtype=torch.float64)
+            for q in range(b - a):
+                assert mine[used] == a + q
+                seg[q] = my_views[used]
+                used += 1
+            parts = [torch.empty_like(seg) for _ in range(world)]
+            dist.all_gather(parts, seg)
+            group = torch.cat(parts)[:g1 - g0]
+            assert not torch.isnan(group).any()
+            for k0, k1 in layers:
+                orc.tsdf_integrate(s.grid, s.rp, s.W, s.H, group.numpy(), None, 0.0, s.K[g0:g1], s.RT[g0:g1], vol, k0, k1)
+        assert used == len(mine)
+        # packed layers -> their places in rank 0's whole-grid volume
+        packed = torch.from_numpy(np.concatenate([vol[k0 * plane:k1 * plane] for k0, k1 in layers]) if layers else np.zeros(0))
         if rank == 0:
+            full = np.zeros(s.grid.n_voxels)
+            for r in range(world):
+                rl = engine.layer_cell_ranges(nz, world, r)
+                n = sum(k1 - k0 for k0, k1 in rl) * plane
+                buf = packed if r == 0 else torch.empty(n, dtype=torch.float64)
+                if r != 0 and n:
+                    dist.recv(buf, src=r)
+                o = 0
+                for k0, k1 in rl:
+                    full[k0 * plane:k1 * plane] = buf[o:o + (k1 - k0) * plane].numpy()
+                    o += (k1 - k0) * plane
             want = orc.tsdf_integrate(s.grid, s.rp, s.W, s.H, s.depths, s.best_cost, 0.14, s.K, s.RT, s.zeros())
-            np.save(out_path, np.stack([full.numpy(), want]))
+            np.save(out_path, np.stack([full, want]))
+        elif packed.numel():
+            dist.send(packed, dst=0)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("group", [2, 4])
-def test_two_ranks_reproduce_the_single_process_volume(tmp_path, group):
+@pytest.mark.parametrize("n_views", [7, 4])
+def test_two_ranks_reproduce_the_single_process_volume(tmp_path, n_views):
     out = str(tmp_path / "vol.npy")
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, group, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, n_views, out), nprocs=2, join=True)
     got, want = np.load(out)
     assert np.count_nonzero(want) > 0
     assert np.array_equal(got, want)
-
-
-def test_view_ownership_covers_every_view_once():
-    from cudadepthmapintegration_b200 import distributed as D
-    for V, G, world in [(1000, 128, 8), (7, 2, 2), (10, 40, 4), (5, 3, 3)]:
-        seen = sorted(v for r in range(world) for v in D.owned_views(V, G, r, world))
-        assert seen == list(range(V))
-        for g0, g1 in D.view_groups(V, G, world):
-            assert (g1 - g0) <= max(world, (G // world) * world)

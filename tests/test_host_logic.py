@@ -2,23 +2,34 @@
 import numpy as np
 import pytest
 
-from cudadepthmapintegration_b200 import sharding, synthetic as syn
+from cudadepthmapintegration_b200 import engine, synthetic as syn
 
 
-@pytest.mark.parametrize("n,world", [(1024, 8), (1024, 3), (7, 8), (1, 2), (100, 1)])
-def test_slab_ranges_partition_the_grid(n, world):
-    r = [sharding.slab_range(n, k, world) for k in range(world)]
-    assert r[0][0] == 0 and r[-1][1] == n
-    for a, b in zip(r, r[1:]):
-        assert a[1] == b[0]
-    assert all(k1 >= k0 for k0, k1 in r)
-    assert max(k1 - k0 for k0, k1 in r) - min(k1 - k0 for k0, k1 in r) <= 1
+@pytest.mark.parametrize("n,world", [(1024, 8), (1024, 3), (100, 8), (33, 2), (7, 8), (1, 2), (100, 1)])
+def test_z_layers_partition_the_grid(n, world):
+    """dmi_set_slab_layers / dmi_shard_initialize: layers of 32 cells dealt round-robin; every plane has one owner and
+    an owner's layers come in increasing order (its packed volume holds them in that order)."""
+    owner = np.full(n, -1)
+    for r in range(world):
+        ranges = engine.layer_cell_ranges(n, world, r)
+        assert ranges == sorted(ranges)
+        for q, (k0, k1) in enumerate(ranges):
+            assert k0 == (q * world + r) * 32 and 0 < k1 - k0 <= 32
+            assert (owner[k0:k1] == -1).all()
+            owner[k0:k1] = r
+    assert (owner >= 0).all()
 
 
-def test_point_and_view_ranges():
-    assert sharding.point_range(10, 0, 4) == (0, 2)
-    assert sharding.point_range(10, 3, 4) == (7, 10)
-    assert sharding.view_range(1000, 7, 8) == (875, 1000)
+@pytest.mark.parametrize("n,world", [(10, 4), (1000, 8), (7, 8), (0, 3), (10_000_000, 8)])
+def test_contiguous_ranges_of_points_and_colour_images(n, world):
+    """dmi_shard_range (coloration: MeshColoration.cxx:140-192 has independent points): contiguous, ordered, complete."""
+    pos = 0
+    for r in range(world):
+        first, count = engine.shard_range(n, world, r)
+        assert first == min(pos, n) and count >= 0
+        pos = first + count
+    assert pos == n
+    assert engine.shard_range(10, 4, 0) == (0, 3) and engine.shard_range(10, 4, 3) == (9, 1)
 
 
 def test_grid_and_potential_follow_survey():
@@ -61,26 +72,24 @@ def test_render_is_device_independent_in_its_random_fields():
     assert np.array_equal(c1.numpy()[1:], c2.numpy())
 
 
-@pytest.mark.parametrize("V,G,world", [(1000, 128, 8), (1000, 128, 2), (100, 16, 4), (7, 4, 1), (10, 128, 2), (64, 64, 8)])
-def test_view_groups_cover_all_views_in_order_with_short_ends(V, G, world):
-    """Groups are consecutive, cover [0, V) once, every size but the last is a multiple of the world size, and
-    with more than one rank both ends are shorter than a full group (integration starts early, the tail is short)."""
-    from cudadepthmapintegration_b200 import distributed as D
-    groups = D.view_groups(V, G, world)
-    assert groups[0][0] == 0 and groups[-1][1] == V
-    for (a0, a1), (b0, b1) in zip(groups, groups[1:]):
-        assert a1 == b0 and a1 > a0
-    assert all((b - a) % world == 0 for a, b in groups[:-1])
-    full = max(world, G // world * world)
-    assert all(b - a <= full for a, b in groups)
-    if world > 1 and V >= 4 * full:
-        assert groups[0][1] - groups[0][0] < full and groups[-1][1] - groups[-1][0] < full
-    # every view has exactly one owner, and owners hold their views in increasing order
-    owners = [v for r in range(world) for v in D.owned_views(V, G, r, world)]
-    assert sorted(owners) == list(range(V))
-    for r in range(world):
-        mine = D.owned_views(V, G, r, world)
+@pytest.mark.parametrize("V,world", [(1000, 8), (1000, 2), (1000, 1), (100, 4), (7, 2), (10, 3), (5, 8), (129, 4), (128, 8)])
+def test_view_ownership_covers_all_views_in_order(V, world):
+    """dmi_shard_view_indices: views go in groups of (128 / world) * world consecutive views; inside a group rank r owns
+    one contiguous share, so that an in-place all-gather assembles the group in list order.  Every view has exactly one
+    owner and owners hold their views in increasing order."""
+    per = max(1, 128 // world)
+    G = per * world
+    owned = [engine.shard_view_indices(V, world, r) for r in range(world)]
+    allv = np.concatenate(owned)
+    assert sorted(allv.tolist()) == list(range(V))
+    for r, mine in enumerate(owned):
         assert list(mine) == sorted(mine)
+        for g0 in range(0, V, G):
+            g1 = min(V, g0 + G)
+            pg = per if g1 - g0 == G else -(-(g1 - g0) // world)
+            in_group = [v for v in mine if g0 <= v < g1]
+            lo = min(g1, g0 + r * pg)
+            assert in_group == list(range(lo, min(g1, lo + pg)))
 
 
 def test_render_views_do_not_depend_on_the_batch():
