@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmi_b200.so")
+# DMI_B200_LIBRARY: another build of the same library (tuning experiments); the default is the in-tree one
+LIB_PATH = os.environ.get("DMI_B200_LIBRARY") or os.path.join(_HERE, "libdmi_b200.so")
 
 DMI_OK = 0
 DMI_ERR_INVALID_ARGUMENT = 1
@@ -74,6 +75,10 @@ _PROTOTYPES = {
     "dmi_color_kernel_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_ll)]),
     "dmi_measure_fp_peak": (C.c_int, [_vp, _i, _d, _pd]),
     "dmi_launch_counter": (C.c_int, [_vp, C.POINTER(_ll)]),
+    "dmi_contour_device": (C.c_int, [_vp, _vp, _i, _d, C.POINTER(_sz), C.POINTER(_sz)]),
+    "dmi_contour": (C.c_int, [_vp, _vp, _i, _d, C.POINTER(_sz), C.POINTER(_sz)]),
+    "dmi_contour_get": (C.c_int, [_vp, _vp, _vp]),
+    "dmi_contour_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_sz)]),
     "dmi_comm_unique_id": (C.c_int, [C.c_char_p]),
     "dmi_comm_init": (C.c_int, [_vp, C.c_char_p, _i, _i]),
     "dmi_comm_destroy": (C.c_int, [_vp]),

@@ -90,6 +90,7 @@ int dmi_destroy(dmi_ctx* ctx)
   ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release();
   ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
   dmi_host::shard_release(ctx);
+  dmi_host::contour_release(ctx);
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
   delete ctx;

@@ -59,6 +59,7 @@ struct KernelStats
 };
 
 struct dmi_shard_state;                // dmi_shard.cu: NCCL communicator, ring of view-group buffers, comm stream
+struct dmi_contour_state;              // dmi_contour.cu: point scalars, scan scratch, the last surface
 
 struct dmi_ctx
 {
@@ -87,6 +88,7 @@ struct dmi_ctx
   int opt_quota = 32;
   std::string err;
   dmi_shard_state* shard = nullptr;    // set by dmi_comm_init
+  dmi_contour_state* contour = nullptr;
 
   int fail(int code, const std::string& msg) { err = msg; return code; }
   int fail_cuda(cudaError_t e, const char* what)
@@ -112,4 +114,5 @@ int integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_depths, co
                             const float* d_tiles, const double* K, const double* RT);
 void set_create_error(const std::string& msg);
 void shard_release(dmi_ctx* ctx);      // dmi_shard.cu: frees ctx->shard (called by dmi_destroy)
+void contour_release(dmi_ctx* ctx);    // dmi_contour.cu: frees ctx->contour (called by dmi_destroy)
 }

@@ -38,6 +38,13 @@
 #include <climits>
 #include <algorithm>
 
+#ifndef DMI_FAST_CTAS
+#define DMI_FAST_CTAS 5          // CTAs of the integration kernel per SM (register cap 65536 / (128 * CTAs))
+#endif
+#ifndef DMI_FAST_HALVES
+#define DMI_FAST_HALVES 2        // 2: gathers of 4 voxels in flight while the other 4 are classified; 1: all 8 at once
+#endif
+
 namespace dmi {
 
 constexpr int FM = 8;                       // voxels per thread, consecutive k
@@ -147,8 +154,8 @@ __device__ __noinline__ T exact_unit(const GridParams* g, const ViewExact* e, co
 
 // T2: FP64 certification of the T1 candidate (pu, pv: centred integer pixel as float).
 // Returns the gather index px - py*W (relative to the last storage row), kReject or kNeedExact.
-__device__ __forceinline__ int tier2(const ViewFast& V, int cxc, int cyc, int W, int H,
-                                     double di, double dj, double dk, float pu, float pv)
+__device__ __noinline__ int tier2(const ViewFast& V, int cxc, int cyc, int W, int H,
+                                  double di, double dj, double dk, float pu, float pv)
 {
   const double hz = affine(V.hz, di, dj, dk);
   if (!(hz > V.m2z)) return (hz < -V.m2z) ? kReject : kNeedExact;            // NaN -> exact
@@ -168,19 +175,26 @@ __device__ __forceinline__ int tier2(const ViewFast& V, int cxc, int cyc, int W,
   return kReject;
 }
 
-// Per-view record in shared memory, written by the pre-pass for the views that survive culling.
+// Per (brick, surviving view) record in shared memory, written by the pre-pass.
 struct __align__(16) ViewSm
 {
-  float4 base;      // brick base of nx, ny, hz (float), zm
-  float4 et;        // Ex, Ey, Tx, Ty: certified iff |eu| < Tx - Ex*r and |ev| < Ty - Ey*r
-  float4 cx;        // fnx[0..2], far threshold (Delta + margin)
-  float4 cy;        // fny[0..2], brick base of camera z (non-pinhole only)
-  float4 cz;        // fhz[0..2], -
-  float4 cc;        // fcz[0..2], - (non-pinhole only)
-  double czr[4];    // camera-z row (FP64)
-  double gd;
+  float4 base;      // brick base of nx, ny, hz (float); brick base of camera z (non-pinhole only)
+  float tcert;      // FP32 tier: certified iff max(|eu|, |ev|) < tcert = min(Tx - Ex*r, Ty - Ey*r) at the brick's largest r
+                    // (-1 when the box's projection cannot be trusted, mode 0: every voxel then goes to the FP64 tier)
+  float thrfar;     // far threshold (Delta + margin)
   int view;
+  int flags;        // bits 0-1: front (see BoxEval); bits 2-3: mode
+  long long voff;   // the view's last storage row in the classification / depth / residual images: npix*v + (H-1)*W
+  int rej;          // gather index (relative to voff) of the spare -1.0f slot
   int pad;
+};
+// Per view of the launch, filled once per CTA from the kernel parameters.
+struct __align__(16) ViewConst
+{
+  float4 cx, cy, cz, cc;   // fnx[0..2], fny[0..2], fhz[0..2], fcz[0..2] (w unused)
+  double czr[4];           // camera-z row (FP64)
+  double gd;
+  float zm, pad;
 };
 
 struct BrickBox { bool valid, inside; float ux, uy; int tx0, tx1, ty0, ty1; };
@@ -266,7 +280,10 @@ __device__ __forceinline__ float footprint_bad(const TilePyramid& pyr, const flo
 // contribution is -Eta*Rho when its pixel is valid and nothing otherwise (:114-115, :202), so phase C only
 // looks at validity.  `front` = 1: moreover every voxel lands inside the image on a valid pixel:
 // the view adds exactly -Eta*Rho to every voxel, no projection needed.
-struct BoxEval { bool keep; int front; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs; };
+// mode 0: nothing known about the box's projection: per-voxel certification, z test and bounds test;
+// mode 1: the projected box is trusted (every voxel has h.z > zm, FP32 error <= 0.24 px at the smallest h.z): one
+//         brick-wide certification threshold, no z test; mode 2: moreover every voxel lands inside the image: no bounds test.
+struct BoxEval { bool keep; int front, mode; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs, rmax; };
 
 template <bool PINHOLE>
 __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& c, const TilePyramid& pyr,
@@ -296,10 +313,17 @@ __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& 
   o.czmaxabs = fmaxf(fabsf(clo), fabsf(chi));
   o.keep = true;
   o.front = 0;
+  o.mode = 0;
+  o.rmax = 0.f;
   BrickBox box; box.valid = false; box.inside = false;
   bool outside = false;
   const bool boxed = brick_box(V, c, o.fbx, o.fby, o.fbz, ei, ej, ek, lx, ly, lz, zlo, W, H, box, outside);
-  if (boxed) { o.Ux = fminf(c.umax1g, box.ux + 1.f); o.Uy = fminf(c.umax1g, box.uy + 1.f); }
+  if (boxed)
+  {
+    o.Ux = fminf(c.umax1g, box.ux + 1.f); o.Uy = fminf(c.umax1g, box.uy + 1.f);
+    o.mode = (box.valid && box.inside) ? 2 : 1;
+    o.rmax = rcp_approx(zlo) * 1.000001f;                     // >= 1 / f_z of every voxel (zlo carries the evaluation slack)
+  }
   if (cull)
   {
     if (zhi < -V.zm) o.keep = false;
@@ -379,238 +403,137 @@ compact_supertiles_kernel(const unsigned* __restrict__ masks, int nst, int useMa
   if (threadIdx.x == 0) { work[0] = s_base; work[1] = 0; }
 }
 
-// One brick (st = supertile, rr = brick within it) against the chunk's views.  All threads of the CTA call it.
-// SPLIT: the double depths are not resident; the band and the exact tier rebuild them from the classification
-// image and the residual image `lo` (split_decode), bit for bit.
-template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
+// One view against the FM voxels of a thread.  INSIDE: every voxel of the brick lands inside the image (mode 2): no bounds
+// test.  front2 (CTA-uniform): the whole brick is certainly farther than Delta in front of every valid depth it can meet,
+// so phase C only looks at the pixel's validity.
+template <typename T, bool PINHOLE, bool COUNT, bool SPLIT, bool INSIDE>
 __device__ __forceinline__ void
-fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ depths, const int* __restrict__ lo,
-           const float* __restrict__ cls, const float* __restrict__ tileDmax, const TilePyramid& pyr, int cull,
-           long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
-           T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters, unsigned st, unsigned rr,
-           ViewSm* s_view, int* s_cnt)
+integrate_view(const GridParams& g, const FastChunk& c, const ViewSm& S, const ViewConst& VC, const double* __restrict__ depths,
+               const int* __restrict__ lo, const float* __restrict__ cls, size_t npix, float fli, float flj,
+               double di, double dj, double dk0, int i, int j, int k0, T nerT, bool front2, T (&acc)[FM], unsigned long long (&cnt)[10])
 {
-  // ---- brick decode (CTA-uniform)
-  const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ;
-  const int bi = (st % nsi) * FSI + rr % FSI;
-  const int bj = ((st / nsi) % nsj) * FSJ + (rr / FSI) % FSJ;
-  const int bk = (st / (nsi * nsj)) * FSK + rr / (FSI * FSJ);
-  if (bi >= nbi || bj >= nbj || bk >= nbk) return;
-  const int i0 = bi * FBI, j0 = bj * FBJ, lp0 = bk * FM, k0 = slab_global_k(g, lp0);     // layers are multiples of FM planes
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int W = g.W, H = g.H;
-
-  // ---- pre-pass: the views the supertile kept are dealt to consecutive threads, one each (dense lanes;
-  // thread order = view order, which the ballot compaction below preserves).  The view is read from the
-  // GLOBAL copy of the chunk: every lane wants a different one, which a constant-bank load would
-  // serialise 32 ways.
-  {
-    unsigned mlo = 0xffffffffu, mhi = 0xffffffffu;
-    if (c.n < 64) { mlo = c.n >= 32 ? 0xffffffffu : ((1u << c.n) - 1u); mhi = c.n > 32 ? ((1u << (c.n - 32)) - 1u) : 0u; }
-    if (cull && stmasks) { mlo &= __ldg(stmasks + 2 * st); mhi &= __ldg(stmasks + 2 * st + 1); }
-    const int ncand = __popc(mlo) + __popc(mhi);
-    const bool have = (int)threadIdx.x < ncand;
-    const int v = have ? nth_set_bit64(mlo, mhi, threadIdx.x) : 0;
-    const ViewFast& V = gviews[v];
-    BoxEval e;
-    e.keep = false;
-    if (have)
-      e = eval_box<PINHOLE>(V, c, pyr, tileDmax + (size_t)v * pyr.perView, i0, j0, k0, (float)(FBI - 1), (float)(FBJ - 1),
-                            (float)(FM - 1), V.lx, V.ly, V.lz, V.lc, W, H, cull != 0);
-    const bool keep = e.keep;
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_cnt[w] = __popc(bal);
-    __syncthreads();
-    if (keep)
-    {
-      int pos = __popc(bal & ((1u << lane) - 1u));
-      for (int q = 0; q < w; q++) pos += s_cnt[q];
-      ViewSm& S = s_view[pos];
-      S.pad = e.front;
-      const float Ex = c.k3 * ((fabsf(e.fbx) + 3.f * V.lx) + e.Ux * (fabsf(e.fbz) + 3.f * V.lz));
-      const float Ey = c.k3 * ((fabsf(e.fby) + 3.f * V.ly) + e.Uy * (fabsf(e.fbz) + 3.f * V.lz));
-      S.base = make_float4(e.fbx, e.fby, e.fbz, V.zm);
-      S.et = make_float4(Ex, Ey, 0.5f - (e.Ux * c.kq + 9.6e-7f), 0.5f - (e.Uy * c.kq + 9.6e-7f));
-      S.cx = make_float4(V.fnx[0], V.fnx[1], V.fnx[2], c.delta_up + 1e-6f * e.czmaxabs);
-      S.cy = make_float4(V.fny[0], V.fny[1], V.fny[2], e.fbc);
-      S.cz = make_float4(V.fhz[0], V.fhz[1], V.fhz[2], 0.f);
-      S.cc = make_float4(V.fcz[0], V.fcz[1], V.fcz[2], 0.f);
-      S.czr[0] = V.cz[0]; S.czr[1] = V.cz[1]; S.czr[2] = V.cz[2]; S.czr[3] = V.cz[3];
-      S.gd = V.gd;
-      S.view = v;
-    }
-  }
-  int nsurv = 0;
-#pragma unroll
-  for (int q = 0; q < FT / 32; q++) nsurv += s_cnt[q];
-  if (nsurv == 0)
-  {
-    if (COUNT && counters && threadIdx.x == 0)
-    {
-      atomicAdd(&counters->culled, (unsigned long long)c.n);
-      atomicAdd(&counters->brick_views, (unsigned long long)c.n);
-    }
-    return;                                                   // the brick's voxels are not even read
-  }
-  __syncthreads();
-  if (COUNT && counters && threadIdx.x == 0)
-  {
-    atomicAdd(&counters->culled, (unsigned long long)(c.n - nsurv));
-    atomicAdd(&counters->brick_views, (unsigned long long)c.n);
-  }
-
-  const int li = (w & 1) * 8 + (lane & 7), lj = (w >> 1) * 4 + (lane >> 3);
-  const int i = i0 + li, j = j0 + lj;
-  if (i >= g.Nx || j >= g.Ny) return;                         // no barrier below
-  const float fli = (float)li, flj = (float)lj;
-  const double di = (double)i, dj = (double)j, dk0 = (double)k0;
-  // voxels beyond the slab's last plane (m >= nk) are computed and discarded: no divergence in the loop
-  const int nk = min(FM, g.nLocal - lp0);
-
-  T acc[FM];
-  const size_t plane = (size_t)g.Nx * g.Ny;
-  T* p = vol + ((size_t)lp0 * g.Ny + j) * g.Nx + i;
-#pragma unroll
-  for (int m = 0; m < FM; m++) acc[m] = (m < nk) ? p[m * plane] : (T)0;
-
-  const size_t npix = (size_t)W * H;
-  const int pxoff = kMagicBits - c.cxc, pyoff = kMagicBits - c.cyc;
+  const float4 b = S.base, cx = VC.cx, cy = VC.cy, cz = VC.cz;
+  // one rounding at base magnitude here, one in the per-voxel FFMA (delta_n = 3 * 2^-24 * ...)
+  const float fnx0 = b.x + fmaf(fli, cx.x, flj * cx.y);
+  const float fny0 = b.y + fmaf(fli, cy.x, flj * cy.y);
+  const float fhz0 = b.z + fmaf(fli, cz.x, flj * cz.y);
+  float fcz0 = 0.f, kc = 0.f;
+  if (!PINHOLE) { const float4 cc = VC.cc; fcz0 = b.w + fmaf(fli, cc.x, flj * cc.y); kc = cc.z; }
+  const float kx = cx.z, ky = cy.z, kz = cz.z;
+  const float thrfar = S.thrfar, tcert = S.tcert;
+  // storage row (H-1-py) of the bottom-up image (CudaReconstruction.cu:141-149): index = px - py*W from there
+  const long long voff = S.voff;
+  const float* cv = cls + voff;
+  asm volatile("" : "+l"(cv));                                // keep it as a plain 64-bit register
+  // rejected voxels gather the spare float behind the classification images, which holds -1.0f:
+  // no predicate, no default value, one sector for the whole warp
+  const int rej = S.rej;
+  // px - py*W = bits(tu) - W*bits(tv) - (pxoff - W*pyoff), all modulo 2^32 (the true index fits an int)
   const int negW = -W;
-  const double delta = g.delta, thick = g.thick;
-  const T nerT = (T)g.neg_eta_rho;
-  unsigned long long n_t1 = 0, n_t2 = 0, n_t3 = 0, n_dg = 0, n_nb = 0, n_uf = 0, n_front = 0, n_behind = 0, n_inv = 0, n_light = 0;
+  const int pxoff = kMagicBits - c.cxc, pyoff = kMagicBits - c.cyc;
+  const int ioff = pxoff + pyoff * negW;
 
-  for (int q = 0; q < nsurv; q++)
+  // Two halves of FM/2 voxels, software-pipelined: A(0) B(0) A(1) B(1) C(0) C(1), so that the gathers
+  // of one half are in flight while the other half is classified.
+  constexpr int NH = DMI_FAST_HALVES, HM = FM / NH;
+  int idx[FM];
+  float d32[FM];
+  unsigned need3 = 0;
+  bool anyh[2] = {false, false};
+#pragma unroll
+  for (int h = 0; h < NH; h++)
   {
-    const ViewSm& S = s_view[q];
-    if (S.pad == 1)                                           // CTA-uniform: the whole brick is free space for this view
+    // ---- phase A: classify HM voxels with the FP32 tier
+    unsigned need = 0;
+    bool anyv = false;
+#pragma unroll
+    for (int mm = 0; mm < HM; mm++)
     {
-#pragma unroll
-      for (int m = 0; m < FM; m++) acc[m] = add_rn(acc[m], nerT);
-      if (COUNT) n_uf++;
-      continue;
-    }
-    const float4 b = S.base, et = S.et, cx = S.cx, cy = S.cy, cz = S.cz;
-    const int v = S.view;
-    // one rounding at base magnitude here, one in the per-voxel FFMA (delta_n = 3 * 2^-24 * ...)
-    const float fnx0 = b.x + fmaf(fli, cx.x, flj * cx.y);
-    const float fny0 = b.y + fmaf(fli, cy.x, flj * cy.y);
-    const float fhz0 = b.z + fmaf(fli, cz.x, flj * cz.y);
-    float fcz0 = 0.f, kc = 0.f;
-    if (!PINHOLE) { const float4 cc = S.cc; fcz0 = cy.w + fmaf(fli, cc.x, flj * cc.y); kc = cc.z; }
-    const float kx = cx.z, ky = cy.z, kz = cz.z;
-    const float zm = b.w, thrfar = cx.w;
-    // storage row (H-1-py) of the bottom-up image (CudaReconstruction.cu:141-149): index = px - py*W from here
-    const size_t voff = npix * v + (size_t)(H - 1) * W;
-    const float* cv = cls + voff;
-    const double* dv = SPLIT ? nullptr : depths + voff;
-    const int* lv = SPLIT ? lo + voff : nullptr;
-    asm volatile("" : "+l"(cv), "+l"(dv), "+l"(lv));          // keep them as plain 64-bit registers
-    // rejected voxels gather the spare float behind the classification images, which holds -1.0f:
-    // no predicate, no default value, one sector for the whole warp
-    const int rej = (int)(clsSpare - (long long)voff);
-
-    // Two halves of FM/2 voxels, software-pipelined: A(0) B(0) A(1) B(1) C(0) C(1), so that the gathers
-    // of one half are in flight while the other half is classified.
-    constexpr int HM = FM / 2;
-    int idx[FM];
-    float d32[FM];
-    unsigned need3 = 0;
-    bool anyh[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-    {
-      // ---- phase A: classify HM voxels with the FP32 tier
-      unsigned need = 0;
-      bool anyv = false;
-#pragma unroll
-      for (int mm = 0; mm < HM; mm++)
+      const int m = h * HM + mm;
+      const float fz = fmaf((float)m, kz, fhz0);
+      const float fx = fmaf((float)m, kx, fnx0);
+      const float fy = fmaf((float)m, ky, fny0);
+      const float r = rcp_approx(fz);
+      const float tu = fmaf(fx, r, kMagic), tv = fmaf(fy, r, kMagic);      // centred pixel, rounded to integer
+      const float pu = tu - kMagic, pv = tv - kMagic;
+      const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);            // distance to that integer
+      // a NaN (only possible where the box is not trusted: tcert = -1) fails the compare or is dropped by the max: either
+      // way nothing is certified against a negative threshold
+      const bool cert = fmaxf(fabsf(eu), fabsf(ev)) < tcert;
+      bool ok;
+      if (INSIDE)
       {
-        const int m = h * HM + mm;
-        const float fz = fmaf((float)m, kz, fhz0);
-        const float fx = fmaf((float)m, kx, fnx0);
-        const float fy = fmaf((float)m, ky, fny0);
-        const float r = rcp_approx(fz);
-        const float tu = fmaf(fx, r, kMagic), tv = fmaf(fy, r, kMagic);      // centred pixel, rounded to integer
-        const float pu = tu - kMagic, pv = tv - kMagic;
-        const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);            // distance to that integer
-        const float tx = fmaf(-et.x, r, et.z), ty = fmaf(-et.y, r, et.w);
-        const bool cert = (fz > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
-        const int px = __float_as_int(tu) - pxoff;
-        const int py = __float_as_int(tv) - pyoff;
-        const bool ok = cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H;
-        idx[m] = ok ? px + py * negW : rej;
-        anyv |= ok;
-        if (!cert) need |= 1u << m;
-        if (COUNT) n_t1 += cert ? 1 : 0;
-      }
-      // ---- rare: voxels the FP32 tier could not certify (and every voxel behind the camera plane).
-      // Dynamic m, so that lanes with different m run the same instructions together.
-      while (need)
-      {
-        const int m = __ffs(need) - 1;
-        need &= need - 1;
-        const float fm = (float)m;
-        const float fz = fmaf(fm, kz, fhz0);
-        int id = kReject;                                                    // certified behind the camera
-        bool okm = false;
-        if (!(fz < -zm))
-        {
-          if (COUNT) n_t2++;
-          const float r = rcp_approx(fz);
-          const float pu = fmaf(fmaf(fm, kx, fnx0), r, kMagic) - kMagic, pv = fmaf(fmaf(fm, ky, fny0), r, kMagic) - kMagic;
-          id = tier2(c.v[v], c.cxc, c.cyc, W, H, di, dj, dk0 + (double)m, pu, pv);
-          if (id == kNeedExact) need3 |= 1u << m;
-          okm = id > kBad;
-        }
-        if (!okm) id = rej;
-#pragma unroll
-        for (int mm = 0; mm < HM; mm++) if (h * HM + mm == m) idx[h * HM + mm] = id;
-        anyv |= okm;
-      }
-      anyh[h] = anyv;
-      // ---- phase B: the half's gathers of the float classification image, all in flight together
-      if (anyv)
-      {
-#pragma unroll
-        for (int mm = 0; mm < HM; mm++) d32[h * HM + mm] = __ldg(cv + idx[h * HM + mm]);
+        ok = cert;
+        idx[m] = ok ? (__float_as_int(tu) + __float_as_int(tv) * negW) - ioff : rej;
       }
       else
       {
-#pragma unroll
-        for (int mm = 0; mm < HM; mm++) d32[h * HM + mm] = -1.0f;
+        const int px = __float_as_int(tu) - pxoff;
+        const int py = __float_as_int(tv) - pyoff;
+        ok = cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H;
+        idx[m] = ok ? px + py * negW : rej;
       }
+      anyv |= ok;
+      if (!cert) need |= 1u << m;
+      if (COUNT) cnt[0] += cert ? 1 : 0;
     }
-    if (need3)                                                               // T3, ~1e-9 of the voxels
+    // ---- rare: voxels the FP32 tier could not certify (and every voxel behind the camera plane).
+    // Dynamic m, so that lanes with different m run the same instructions together.
+    while (need)
     {
-#pragma unroll
-      for (int m = 0; m < FM; m++)
-        if (need3 & (1u << m))
-        {
-          if (COUNT) n_t3++;
-          acc[m] = exact_unit<T>(&g, &c.e[v], SPLIT ? nullptr : depths + npix * v, cls + npix * v,
-                                 SPLIT ? lo + npix * v : nullptr, i, j, k0 + m, acc[m]);
-        }
-    }
-    if (!anyh[0] && !anyh[1]) continue;
-
-    if (S.pad == 2)                                            // CTA-uniform: only validity matters for this view
-    {
-#pragma unroll
-      for (int m = 0; m < FM; m++)
+      const int m = __ffs(need) - 1;
+      need &= need - 1;
+      const float fm = (float)m;
+      const float fz = fmaf(fm, kz, fhz0);
+      int id = kReject;                                                    // certified behind the camera
+      bool okm = false;
+      if (!(fz < -VC.zm))
       {
-        add_if_valid(acc[m], nerT, d32[m]);
-        if (COUNT) { if (d32[m] == -1.0f) n_inv++; else { n_front++; n_light++; } }
+        if (COUNT) cnt[1]++;
+        const float r = rcp_approx(fz);
+        const float pu = fmaf(fmaf(fm, kx, fnx0), r, kMagic) - kMagic, pv = fmaf(fmaf(fm, ky, fny0), r, kMagic) - kMagic;
+        id = tier2(c.v[S.view], c.cxc, c.cyc, W, H, di, dj, dk0 + (double)m, pu, pv);
+        if (id == kNeedExact) need3 |= 1u << m;
+        okm = id > kBad;
       }
-      continue;
+      if (!okm) id = rej;
+#pragma unroll
+      for (int mm = 0; mm < HM; mm++) if (h * HM + mm == m) idx[h * HM + mm] = id;
+      anyv |= okm;
     }
+    anyh[h] = anyv;
+    // ---- phase B: the half's gathers of the float classification image, all in flight together
+    if (anyv)
+    {
+#pragma unroll
+      for (int mm = 0; mm < HM; mm++) d32[h * HM + mm] = __ldg(cv + idx[h * HM + mm]);
+    }
+    else
+    {
+#pragma unroll
+      for (int mm = 0; mm < HM; mm++) d32[h * HM + mm] = -1.0f;
+    }
+  }
+  if (!need3 && !anyh[0] && !anyh[1]) return;
 
+  unsigned near = 0;
+  if (front2)                                                              // only validity matters for this view
+  {
+#pragma unroll
+    for (int m = 0; m < FM; m++)
+    {
+      add_if_valid(acc[m], nerT, d32[m]);
+      if (COUNT) { if (d32[m] == -1.0f) cnt[7]++; else { cnt[5]++; cnt[9]++; } }
+    }
+  }
+  else
+  {
     // ---- phase C: FP32 classification; -1.0f = invalid after the filter (:202).  In front and farther
     // than Delta (certified by the margin in thrfar): -Eta*Rho; behind and farther: 0 (:114-115);
     // everything else that is valid (NaN included) goes to the FP64 band below.
-    unsigned near = 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++)
+    for (int h = 0; h < NH; h++)
     {
       if (anyh[h])
       {
@@ -623,66 +546,211 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
           if (COUNT)
           {
             const float df = fc - d32[m];
-            if (d32[m] == -1.0f) n_inv++;
-            else if (fabsf(df) > thrfar) { if (df < 0.f) n_front++; else n_behind++; }
-          }
-        }
-      }
-    }
-    // ---- the band around the surface: double depth, FP64 potential
-    if (near)
-    {
-      const double zij = __fma_rn(di, S.czr[0], __fma_rn(dj, S.czr[1], S.czr[3]));
-      const double czk = S.czr[2], gd = S.gd;
-      double dd[FM];
-#pragma unroll
-      for (int m = 0; m < FM; m++)
-      {
-        if (SPLIT) dd[m] = (near & (1u << m)) ? split_decode(d32[m], __ldg(lv + idx[m])) : 0.0;
-        else dd[m] = (near & (1u << m)) ? __ldg(dv + idx[m]) : 0.0;
-      }
-#pragma unroll
-      for (int m = 0; m < FM; m++)
-      {
-        if (near & (1u << m))
-        {
-          if (COUNT) n_nb++;
-          // explicit roundings: the value of a voxel must not depend on which unrolled copy (m) or
-          // brick decomposition evaluates it, so that z-slabs concatenate bit-identically
-          const double z = __fma_rn(dk0 + (double)m, czk, zij);              // :207, from GLOBAL indices
-          const double diff = __dsub_rn(z, dd[m]);
-          const double ad = fabs(diff);
-          const double td = __dsub_rn(ad, delta);
-          if (fabs(td) < gd)
-          {
-            if (COUNT) n_dg++;
-            acc[m] = exact_unit<T>(&g, &c.e[v], SPLIT ? nullptr : depths + npix * v, cls + npix * v,
-                                   SPLIT ? lo + npix * v : nullptr, i, j, k0 + m, acc[m]);
-          }
-          else if (td > 0.0)
-          {
-            if (!(diff > 0.0)) acc[m] = add_rn(acc[m], nerT);                // :114-115
-          }
-          else
-          {
-            const double res = (ad > thick) ? (diff > 0.0 ? g.rho : -g.rho)  // :116-117
-                                            : __dmul_rn(g.rho_over_thick, diff);   // :118-119
-            acc[m] = add_rn(acc[m], (T)res);                                  // :211
+            if (d32[m] == -1.0f) cnt[7]++;
+            else if (fabsf(df) > thrfar) { if (df < 0.f) cnt[5]++; else cnt[6]++; }
           }
         }
       }
     }
   }
+  // ---- the band around the surface (a shell 2*Delta thick: whole bricks are in it or not): double depth, FP64
+  // potential, inline and predicated
+  if (near)
+  {
+    const double* dv = SPLIT ? nullptr : depths + voff;
+    const int* lv = SPLIT ? lo + voff : nullptr;
+    // explicit roundings: the value of a voxel must not depend on which unrolled copy (m) or brick decomposition
+    // evaluates it, so that z-slabs concatenate bit-identically
+    const double zij = __fma_rn(di, VC.czr[0], __fma_rn(dj, VC.czr[1], VC.czr[3]));
+    const double czk = VC.czr[2], gd = VC.gd;
+    const double delta = g.delta, thick = g.thick, rho = g.rho, rot = g.rho_over_thick;
+    double dd[FM];
 #pragma unroll
-  for (int m = 0; m < FM; m++)
-    if (m < nk) p[m * plane] = acc[m];
+    for (int m = 0; m < FM; m++)
+    {
+      if (SPLIT) dd[m] = (near & (1u << m)) ? split_decode(d32[m], __ldg(lv + idx[m])) : 0.0;
+      else dd[m] = (near & (1u << m)) ? __ldg(dv + idx[m]) : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < FM; m++)
+    {
+      if (near & (1u << m))
+      {
+        if (COUNT) cnt[4]++;
+        const double z = __fma_rn(dk0 + (double)m, czk, zij);              // :207, from GLOBAL indices
+        const double diff = __dsub_rn(z, dd[m]);
+        const double ad = fabs(diff);
+        const double td = __dsub_rn(ad, delta);
+        if (fabs(td) < gd) need3 |= 1u << m;                                // within 2^-44 of the discontinuity: exact tier
+        else if (td > 0.0)
+        {
+          if (!(diff > 0.0)) acc[m] = add_rn(acc[m], nerT);                // :114-115
+        }
+        else
+        {
+          const double res = (ad > thick) ? (diff > 0.0 ? rho : -rho)      // :116-117
+                                          : __dmul_rn(rot, diff);          // :118-119
+          acc[m] = add_rn(acc[m], (T)res);                                  // :211
+        }
+        if (COUNT && fabs(td) < gd) cnt[3]++;
+      }
+    }
+  }
+  // ---- T3: the reference's own operation sequence (~1e-9 of the voxels), one copy of the call
+  while (need3)
+  {
+    const int m = __ffs(need3) - 1;
+    need3 &= need3 - 1;
+    if (COUNT) cnt[2]++;
+    T a = (T)0;
+#pragma unroll
+    for (int mm = 0; mm < FM; mm++) if (mm == m) a = acc[mm];
+    const int v = S.view;
+    a = exact_unit<T>(&g, &c.e[v], SPLIT ? nullptr : depths + npix * v, cls + npix * v, SPLIT ? lo + npix * v : nullptr, i, j,
+                      k0 + m, a);
+#pragma unroll
+    for (int mm = 0; mm < FM; mm++) if (mm == m) acc[mm] = a;
+  }
+}
+
+constexpr int kColBricks = FSK;   // bricks of one work item: a column of the supertile along k (16 x 8 x 32 voxels)
+
+// One work item = the FSK bricks of a supertile column against the chunk's views.  All threads of the CTA call it.
+//   pre-pass   warp w examines brick w of the column: lane l takes the candidate views l and l + 32 (the views the
+//              supertile kept), so that the dependent chain of the brick test (view record -> FP64 bases -> 8
+//              reciprocals -> footprint tables) is paid once per FOUR bricks and by all four warps at once
+//   main loop  brick after brick, all 128 threads, each view of the brick's list against 8 voxels per thread
+// SPLIT: the double depths are not resident; the band and the exact tier rebuild them from the classification
+// image and the residual image `lo` (split_decode), bit for bit.
+template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
+__device__ __forceinline__ void
+fast_column(const GridParams& g, const FastChunk& c, const double* __restrict__ depths, const int* __restrict__ lo,
+            const float* __restrict__ cls, const float* __restrict__ tileDmax, const TilePyramid& pyr, int cull,
+            long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
+            T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters, unsigned st, unsigned col,
+            ViewSm (*s_view)[kFastChunk], const ViewConst* s_const, int* s_cnt)
+{
+  // ---- column decode (CTA-uniform)
+  const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ;
+  const int bi = (st % nsi) * FSI + col % FSI;
+  const int bj = ((st / nsi) % nsj) * FSJ + col / FSI;
+  const int bk0 = (st / (nsi * nsj)) * FSK;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int W = g.W, H = g.H;
+  const bool colValid = bi < nbi && bj < nbj;
+  const int i0 = bi * FBI, j0 = bj * FBJ;
+  const long long npixAll = (long long)W * H;
+
+  // ---- pre-pass: warp w <-> brick bk0 + w; thread order = view order, which the ballot compaction preserves.
+  // The view is read from the GLOBAL copy of the chunk: every lane wants a different one, which a constant-bank
+  // load would serialise 32 ways.
+  {
+    static_assert(kColBricks == FT / 32, "one warp per brick of the column");
+    unsigned mlo = 0xffffffffu, mhi = 0xffffffffu;
+    if (c.n < 64) { mlo = c.n >= 32 ? 0xffffffffu : ((1u << c.n) - 1u); mhi = c.n > 32 ? ((1u << (c.n - 32)) - 1u) : 0u; }
+    if (cull && stmasks) { mlo &= __ldg(stmasks + 2 * st); mhi &= __ldg(stmasks + 2 * st + 1); }
+    const int ncand = __popc(mlo) + __popc(mhi);
+    const bool brickValid = colValid && bk0 + w < nbk;
+    const int k0 = slab_global_k(g, (bk0 + w) * FM);
+    int n = 0;
+    for (int r0 = 0; r0 < ncand && brickValid; r0 += 32)
+    {
+      const int cand = r0 + lane;
+      const bool have = cand < ncand;
+      const int v = have ? nth_set_bit64(mlo, mhi, cand) : 0;
+      const ViewFast& V = gviews[v];
+      BoxEval e;
+      e.keep = false;
+      if (have)
+        e = eval_box<PINHOLE>(V, c, pyr, tileDmax + (size_t)v * pyr.perView, i0, j0, k0, (float)(FBI - 1), (float)(FBJ - 1),
+                              (float)(FM - 1), V.lx, V.ly, V.lz, V.lc, W, H, cull != 0);
+      const unsigned bal = __ballot_sync(0xffffffffu, e.keep);
+      if (e.keep)
+      {
+        ViewSm& S = s_view[w][n + __popc(bal & ((1u << lane) - 1u))];
+        const float Ex = c.k3 * ((fabsf(e.fbx) + 3.f * V.lx) + e.Ux * (fabsf(e.fbz) + 3.f * V.lz));
+        const float Ey = c.k3 * ((fabsf(e.fby) + 3.f * V.ly) + e.Uy * (fabsf(e.fbz) + 3.f * V.lz));
+        const float Tx = 0.5f - (e.Ux * c.kq + 9.6e-7f), Ty = 0.5f - (e.Uy * c.kq + 9.6e-7f);
+        S.base = make_float4(e.fbx, e.fby, e.fbz, e.fbc);
+        // the per-voxel bound T - E*r (certification) at the largest r of the brick, rounded down
+        S.tcert = e.mode ? fminf(fmaf(-Ex, e.rmax, Tx), fmaf(-Ey, e.rmax, Ty)) - 1e-7f : -1.f;
+        S.thrfar = c.delta_up + 1e-6f * e.czmaxabs;
+        S.view = v;
+        S.flags = e.front | (e.mode << 2);
+        S.voff = (long long)npixAll * v + (long long)(H - 1) * W;
+        S.rej = (int)(clsSpare - S.voff);
+        S.pad = 0;
+      }
+      n += __popc(bal);
+    }
+    if (lane == 0) s_cnt[w] = n;
+  }
+  __syncthreads();
+  if (COUNT && counters && threadIdx.x == 0)
+  {
+    int nb = 0, ns = 0;
+    for (int q = 0; q < kColBricks; q++) if (colValid && bk0 + q < nbk) { nb++; ns += s_cnt[q]; }
+    atomicAdd(&counters->culled, (unsigned long long)(nb * c.n - ns));
+    atomicAdd(&counters->brick_views, (unsigned long long)(nb * c.n));
+  }
+  if (!colValid) return;
+
+  const int li = (w & 1) * 8 + (lane & 7), lj = (w >> 1) * 4 + (lane >> 3);
+  const int i = i0 + li, j = j0 + lj;
+  if (i >= g.Nx || j >= g.Ny) return;                         // no barrier below
+  const float fli = (float)li, flj = (float)lj;
+  const double di = (double)i, dj = (double)j;
+  const size_t plane = (size_t)g.Nx * g.Ny, npix = (size_t)W * H;
+  const T nerT = (T)g.neg_eta_rho;
+  unsigned long long cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // t1, t2, t3, delta guard, band, front, behind, invalid, -, validity-only
+  unsigned long long n_units = 0, n_uf = 0;
+
+#pragma unroll 1
+  for (int q = 0; q < kColBricks; q++)
+  {
+    const int nsurv = s_cnt[q];
+    if (nsurv == 0 || bk0 + q >= nbk) continue;               // the brick's voxels are not even read
+    const int lp0 = (bk0 + q) * FM, k0 = slab_global_k(g, lp0);
+    const double dk0 = (double)k0;
+    // voxels beyond the slab's last plane (m >= nk) are computed and discarded: no divergence in the loop
+    const int nk = min(FM, g.nLocal - lp0);
+    T acc[FM];
+    T* p = vol + ((size_t)lp0 * g.Ny + j) * g.Nx + i;
+#pragma unroll
+    for (int m = 0; m < FM; m++) acc[m] = (m < nk) ? p[m * plane] : (T)0;
+
+#pragma unroll 1
+    for (int s = 0; s < nsurv; s++)
+    {
+      const ViewSm& S = s_view[q][s];
+      const int flags = S.flags;                              // CTA-uniform
+      if ((flags & 3) == 1)                                   // the whole brick is free space for this view
+      {
+#pragma unroll
+        for (int m = 0; m < FM; m++) acc[m] = add_rn(acc[m], nerT);
+        if (COUNT) n_uf += nk;
+        continue;
+      }
+      if (COUNT) n_units += nk;
+      const ViewConst& VC = s_const[S.view];
+      const bool f2 = (flags & 3) == 2;
+      if ((flags >> 2) == 2)
+        integrate_view<T, PINHOLE, COUNT, SPLIT, true>(g, c, S, VC, depths, lo, cls, npix, fli, flj, di, dj, dk0, i, j, k0, nerT, f2,
+                                                       acc, cnt);
+      else
+        integrate_view<T, PINHOLE, COUNT, SPLIT, false>(g, c, S, VC, depths, lo, cls, npix, fli, flj, di, dj, dk0, i, j, k0, nerT, f2,
+                                                        acc, cnt);
+    }
+#pragma unroll
+    for (int m = 0; m < FM; m++)
+      if (m < nk) p[m * plane] = acc[m];
+  }
 
   if (COUNT && counters)
   {
     // one atomic per warp and counter (the lanes that returned early above are simply absent)
     const unsigned act = __activemask();
-    unsigned long long vals[11] = {n_t1, n_t2, n_t3, n_dg, n_nb, (unsigned long long)nk * (nsurv - n_uf), n_front, n_behind, n_inv,
-                                   (unsigned long long)nk * n_uf, n_light};
+    unsigned long long vals[11] = {cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], n_units, cnt[5], cnt[6], cnt[7], n_uf, cnt[9]};
 #pragma unroll
     for (int q = 0; q < 11; q++)
     {
@@ -711,15 +779,13 @@ fast_brick(const GridParams& g, const FastChunk& c, const double* __restrict__ d
   }
 }
 
-// Persistent kernel: as many CTAs as fit the GPU; each takes the next brick of the next ACTIVE supertile from a
+// Persistent kernel: as many CTAs as fit the GPU; each takes the next column of the next ACTIVE supertile from a
 // global counter until none is left (a launch over all bricks would spend ~2 ns on each of the many bricks
-// no view of the chunk can touch).  5 CTAs per SM (96 registers, ~130 bytes of spills in the rare tiers):
-// measured on config5, ms per step at 3 / 4 / 5 / 6 CTAs per SM = 292 / 254 / 238 / 246 -- the gathers'
-// latency wants warps more than the loop wants registers.  A CTA retires after kBrickQuota bricks, so that
-// higher-priority kernels of other streams (the next views' preparation, NCCL) find a free slot within a
-// fraction of a millisecond instead of waiting for the whole launch (quota: DMI_OPT_BRICK_QUOTA).
+// no view of the chunk can touch).  The next item is fetched while the current one is integrated.  A CTA retires after
+// `quota` items, so that higher-priority kernels of other streams (the next views' preparation, NCCL) find a free slot
+// within a fraction of a millisecond instead of waiting for the whole launch (DMI_OPT_BRICK_QUOTA, in bricks).
 template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
-__global__ void __launch_bounds__(FT, 5)
+__global__ void __launch_bounds__(FT, DMI_FAST_CTAS)
 tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
                  const double* __restrict__ depths, const int* __restrict__ lo, const float* __restrict__ cls,
                  const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
@@ -727,21 +793,37 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
                  const int* __restrict__ stlist, int* __restrict__ work, int quota,
                  T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters)
 {
-  static_assert(kFastChunk <= FT, "one pre-pass thread per view");
-  __shared__ ViewSm s_view[kFastChunk];
-  __shared__ int s_cnt[FT / 32];
-  __shared__ int s_item;
-  constexpr int per = FSI * FSJ * FSK;
+  static_assert(kFastChunk <= 64, "two rounds of 32 candidate views per brick");
+  __shared__ ViewSm s_view[kColBricks][kFastChunk];
+  __shared__ ViewConst s_const[kFastChunk];
+  __shared__ int s_cnt[kColBricks];
+  __shared__ int s_item[2];
+  constexpr int per = FSI * FSJ;
   const int nItems = work[0] * per;
-  for (int it = 0; it < quota; it++)
+  if ((int)threadIdx.x < c.n)
   {
-    __syncthreads();                                          // the previous brick is done with shared memory
-    if (threadIdx.x == 0) s_item = atomicAdd(work + 1, 1);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= nItems) break;
-    fast_brick<T, PINHOLE, COUNT, SPLIT>(g, c, depths, lo, cls, tileDmax, pyr, cull, clsSpare, gviews, stmasks, vol, nbi, nbj, nbk,
-                                         counters, (unsigned)__ldg(stlist + item / per), (unsigned)(item % per), s_view, s_cnt);
+    // from the GLOBAL copy: one view per thread out of the constant bank would be serialised 64 ways
+    const ViewFast& V = gviews[threadIdx.x];
+    ViewConst& K = s_const[threadIdx.x];
+    K.cx = make_float4(V.fnx[0], V.fnx[1], V.fnx[2], 0.f);
+    K.cy = make_float4(V.fny[0], V.fny[1], V.fny[2], 0.f);
+    K.cz = make_float4(V.fhz[0], V.fhz[1], V.fhz[2], 0.f);
+    K.cc = make_float4(V.fcz[0], V.fcz[1], V.fcz[2], 0.f);
+    K.czr[0] = V.cz[0]; K.czr[1] = V.cz[1]; K.czr[2] = V.cz[2]; K.czr[3] = V.cz[3];
+    K.gd = V.gd;
+    K.zm = V.zm; K.pad = 0.f;
+  }
+  if (threadIdx.x == 0) s_item[0] = atomicAdd(work + 1, 1);
+  __syncthreads();
+  int item = s_item[0];
+  for (int it = 0; it < quota && item < nItems; it++)
+  {
+    // the next item's number arrives while this one is integrated (a CTA about to retire takes none)
+    if (threadIdx.x == 0) s_item[(it + 1) & 1] = (it + 1 < quota) ? atomicAdd(work + 1, 1) : nItems;
+    fast_column<T, PINHOLE, COUNT, SPLIT>(g, c, depths, lo, cls, tileDmax, pyr, cull, clsSpare, gviews, stmasks, vol, nbi, nbj, nbk,
+                                          counters, (unsigned)__ldg(stlist + item / per), (unsigned)(item % per), s_view, s_const, s_cnt);
+    __syncthreads();                                          // this item is done with shared memory
+    item = s_item[(it + 1) & 1];
   }
 }
 
@@ -758,7 +840,7 @@ __global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant_
   if ((int)threadIdx.x < c.n) dst[threadIdx.x].pad[0] = tiles[(size_t)threadIdx.x * perView + flagOff];
 }
 
-// Enough CTAs to take every brick at `quota` each, at least as many as are resident at once on this device
+// Enough CTAs to take every work item at `quota` each, at least as many as are resident at once on this device
 static unsigned persistent_grid(const void* kernel, unsigned bricks, unsigned quota)
 {
   int dev = 0, sms = 0, perSm = 0;
@@ -776,6 +858,8 @@ static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& 
                            int nbk, FastCounters* d_counters, int quota, cudaStream_t s)
 {
   const int nst = (int)(grid / (FSI * FSJ * FSK));
+  grid /= kColBricks;                                         // work items = supertile columns of FSK bricks
+  quota = std::max(1, quota / kColBricks);
   if (cull)
     supertile_cull_kernel<PINHOLE><<<(nst + 3) / 4, 256, 0, s>>>(g, c, d_tileDmax, pyr, d_views, nbi, nbj, nbk, d_masks, nst);
   const unsigned* masks = cull ? d_masks : nullptr;

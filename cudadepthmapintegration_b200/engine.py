@@ -284,6 +284,33 @@ class Context:
                                                _ptr(int(d_colors)), _ptr(K), _ptr(RT), int(width), int(height),
                                                _ptr(int(d_mean)), _ptr(int(d_median)), _ptr(int(d_nb))))
 
+    # -- isosurface of the fused volume (Reconstruction/main.cxx:151-189) ---------------------------
+    def contour_device(self, d_cell_scalars: int | None, dtype, value: float):
+        """Surface of the cell scalars at d_cell_scalars (None: the context's own volume); returns (nVertices, nTriangles)."""
+        nv, nt = C.c_size_t(), C.c_size_t()
+        self._ck(self._lib.dmi_contour_device(self._h, _ptr(int(d_cell_scalars)) if d_cell_scalars else None,
+                                              scalar_code(dtype), float(value), C.byref(nv), C.byref(nt)))
+        return int(nv.value), int(nt.value)
+
+    def contour(self, cell_scalars: np.ndarray, value: float):
+        """vtkCellDataToPointData + contour + grid matrix on host cell scalars; returns (vertices f32 [n,3], triangles i32 [m,3])."""
+        cs = np.ascontiguousarray(cell_scalars)
+        nv, nt = C.c_size_t(), C.c_size_t()
+        self._ck(self._lib.dmi_contour(self._h, _ptr(cs), scalar_code(cs.dtype), float(value), C.byref(nv), C.byref(nt)))
+        return self.contour_get(int(nv.value), int(nt.value))
+
+    def contour_get(self, n_vertices: int, n_triangles: int):
+        v = np.empty((n_vertices, 3), dtype=np.float32)
+        t = np.empty((n_triangles, 3), dtype=np.int32)
+        self._ck(self._lib.dmi_contour_get(self._h, _ptr(v), _ptr(t)))
+        return v, t
+
+    def contour_device_ptr(self):
+        pv, pt = C.c_void_p(), C.c_void_p()
+        nv, nt = C.c_size_t(), C.c_size_t()
+        self._ck(self._lib.dmi_contour_device_ptr(self._h, C.byref(pv), C.byref(pt), C.byref(nv), C.byref(nt)))
+        return int(pv.value or 0), int(pt.value or 0), int(nv.value), int(nt.value)
+
     def color_kernel_stats(self):
         ms = C.c_float()
         n = C.c_longlong()

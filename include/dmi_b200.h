@@ -200,6 +200,29 @@ int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyz
                         uint8_t* d_mean, uint8_t* d_median, int32_t* d_nbProjected);
 int dmi_color_kernel_stats(dmi_ctx* ctx, float* ms, long long* launches);
 
+/* ---- isosurface of the fused volume (the stage after the path: Reconstruction/main.cxx:151-189) -----------
+ *
+ * vtkCellDataToPointData -> vtkContourFilter(--contour) -> vtkTransformFilter(grid matrix) of the reference's CLI, on
+ * the GPU, so that the fused volume (8.6 GB at 1024^3) need not travel to the host and dmi_colorize_device can take its
+ * points from device memory.  Grid geometry = the one given to dmi_initialize.
+ *   point scalars  average of the cells sharing the point (double)
+ *   vertices       float32 world coordinates, one per grid edge whose ends differ in (scalar >= value); numbered by owning
+ *                  point (k, j, i order), then axis -- the vertex set any edge-based contouring yields
+ *   triangles      int32 vertex ids, per cell in k, j, i order, watertight, normals from inside (>= value) to outside;
+ *                  the triangulation is this library's own (csrc/dmi_contour.cu), not VTK's
+ * dmi_contour_device   d_cellScalars = NULL: the context's own volume (it must cover the whole grid).  Synchronous
+ *                      (the counts come back to the host); the surface stays on the device until the next call.
+ * dmi_contour          the same from host memory (cell scalars of the whole grid, VTK cell order)
+ * dmi_contour_get      copies the last surface to host memory (either pointer may be NULL)
+ * dmi_contour_device_ptr  device addresses of the last surface (valid until the next dmi_contour* / dmi_destroy)   */
+int dmi_contour_device(dmi_ctx* ctx, const void* d_cellScalars, int scalarType, double value,
+                       size_t* nVertices, size_t* nTriangles);
+int dmi_contour(dmi_ctx* ctx, const void* cellScalars, int scalarType, double value,
+                size_t* nVertices, size_t* nTriangles);
+int dmi_contour_get(dmi_ctx* ctx, float* vertices, int32_t* triangles);
+int dmi_contour_device_ptr(dmi_ctx* ctx, const float** d_vertices, const int32_t** d_triangles,
+                           size_t* nVertices, size_t* nTriangles);
+
 /* ---- sharding over several GPUs (new; the reference is single-GPU) ---------------------------------
  *
  * The grid is cut into z-layers of 32 cells dealt round-robin to the GPUs (dmi_set_slab_layers): every voxel has one
