@@ -62,7 +62,10 @@ def parse_args():
     ap.add_argument("--breakdown", action="store_true", help="N>1: add the per-rank compute / gather spans of the last step to the line")
     ap.add_argument("--cost-model", default="iid", choices=["iid", "coherent"],
                     help="synthetic best-cost maps: independent per pixel (default, the headline workload) or spatially coherent")
-    ap.add_argument("--color-points", type=int, default=10000000)
+    ap.add_argument("--color-points", type=int, default=0,
+                    help="0 (default): colour the vertices of the isosurface of the fused volume (GPU contour, value --contour); "
+                         "> 0: that many points on the unit sphere instead")
+    ap.add_argument("--contour", type=float, default=1.0, help="isosurface value (Reconstruction/main.cxx:80)")
     ap.add_argument("--color-views", type=int, default=1000)
     return ap.parse_args()
 
@@ -216,13 +219,21 @@ def mesh_points(P):
     return np.ascontiguousarray(pts[order].astype(np.float32))
 
 
-def measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak, fp32_peak, timed, steps=3, warmup=2):
+def measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak, fp32_peak, timed, mesh, steps=3, warmup=2):
     """Secondary metric (BASELINE.json): colored points/sec at config 5's shape (~10 M points x 1000 views).  N>1: points
     sharded by contiguous index range (dmi_shard_range), every rank renders ("loads") one block of the colour images and
     the library all-gathers them with NCCL inside the timed region (dmi_shard_colorize_device)."""
     from cudadepthmapintegration_b200 import engine, synthetic as syn
     from tests import _oracle
-    P, V = args.color_points, args.color_views
+    V = args.color_views
+    if mesh is not None:
+        pts_h = mesh.cpu().numpy()                          # the isosurface's vertices, in the contour's own order
+        mesh_text = "isosurface vertices of the fused volume (GPU contour, float32, contour order)"
+    else:
+        pts_h = mesh_points(args.color_points)
+        mesh_text = "points on the unit sphere (scanline order, float32)"
+    P = pts_h.shape[0]
+    mesh = None
     K, RT = syn.make_cameras(V, W, H)
     v0, nv = engine.shard_range(V, world, rank)
     p0, npts = engine.shard_range(P, world, rank)
@@ -231,7 +242,6 @@ def measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak
         m = min(8, nv - q)
         _, _, c = syn.render_views(K[v0 + q:v0 + q + m], RT[v0 + q:v0 + q + m], W, H, first_view=v0 + q, device=dev, want_best_cost=False)
         cols[q:q + m] = c
-    pts_h = mesh_points(P)
     pts = torch.from_numpy(pts_h[p0:p0 + npts]).to(dev)
     mean = torch.zeros((max(npts, 1), 3), dtype=torch.uint8, device=dev)
     med = torch.zeros_like(mean)
@@ -270,7 +280,7 @@ def measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak
     out = {"metric": "colored points/sec", "value": P / (ms * 1e-3), "unit": "points/s", "point_views_per_s": P * V / (ms * 1e-3),
            "n_gpus": world, "ms_per_step": ms, "steps": steps, "warmup": warmup, "kernel_ms_per_step": kms / max(kn, 1),
            "result_digest": digest,
-           "config": {"workload": f"mesh coloration {P} points (sphere, scanline order, float32) x {V} views {W}x{H}",
+           "config": {"workload": f"mesh coloration {P} points x {V} views {W}x{H}; mesh = {mesh_text}",
                       "parallelism": "one GPU" if world == 1 else f"points sharded by contiguous index range over {world} GPUs; colour images "
                                      "all-gathered with NCCL inside the timed region (dmi_shard_colorize_device)",
                       "l2": "colour images (%.1f GB) exceed L2; no flush needed" % (3.0 * V * W * H / 1e9)},
@@ -633,6 +643,36 @@ def main():
     if not args.no_e2e:
         e2e, host_bufs = measure_e2e(args, ctx, torch, dev, rank, world, N, V, W, H, K, RT, my_depths, my_cost, slab_cells, units, timed)
 
+    # ---- the stage after the path (Reconstruction/main.cxx:151-189): isosurface of the fused volume, on the GPU; its vertices
+    # are the mesh the coloration benchmark colours (BASELINE config 5: "coloration of the extracted ~10M-point mesh")
+    contour, mesh = None, None
+    if not args.no_coloration and not args.emulate_rank and args.color_points == 0:
+        step_device()
+        barrier()
+        if rank == 0:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nv, nt = ctx.contour_device(full_volume.data_ptr() if world > 1 else None, np.float64, args.contour)
+            e1.record()
+            torch.cuda.synchronize()
+            pv, _, _, _ = ctx.contour_device_ptr()
+
+            class _M:
+                pass
+            hm = _M()
+            hm.__cuda_array_interface__ = {"shape": (nv, 3), "typestr": "<f4", "data": (pv, False), "version": 3}
+            mesh = torch.as_tensor(hm, device=dev).clone()
+            contour = {"ms": e0.elapsed_time(e1), "vertices": nv, "triangles": nt, "value": args.contour,
+                       "what": "dmi_contour_device on the fused volume in device memory: cell -> point averaging, surface vertices (float32, "
+                               "grid matrix applied), triangles; 5 kernels + 2 scans, counts read back to the host in between",
+                       "instead_of": "D2H of the %.1f GB volume + host vtkCellDataToPointData / vtkContourFilter" % (N ** 3 * 8 / 1e9)}
+        if world > 1:
+            shape = [tuple(mesh.shape) if rank == 0 else None]
+            dist.broadcast_object_list(shape, src=0)
+            if rank != 0:
+                mesh = torch.empty(shape[0], dtype=torch.float32, device=dev)
+            dist.broadcast(mesh, src=0)
+
     # ---- B1: the reference's own CUDA kernel on this GPU, driven like ProcessDepthMap (N=1 only: it has no multi-GPU path)
     reference_cuda = None
     if world == 1 and not args.no_reference_cuda and not args.emulate_rank and args.kernel != "exact":
@@ -651,7 +691,7 @@ def main():
         host_bufs = None
         full_volume = None
         torch.cuda.empty_cache()
-        coloration = measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak, fp32_peak, timed)
+        coloration = measure_coloration(args, ctx, torch, dist, dev, rank, world, W, H, fp64_peak, fp32_peak, timed, mesh)
 
     if rank == 0:
         peaks = {}
@@ -725,6 +765,8 @@ def main():
             line["reference_cuda"] = reference_cuda
         if variants is not None:
             line["variants"] = variants
+        if contour is not None:
+            line["contour"] = contour
         if coloration is not None:
             line["coloration"] = coloration
         if not args.no_cpu_baseline and world == 1:

@@ -29,7 +29,7 @@
 
 namespace dmi {
 
-constexpr int kColorWarps = 8;     // warps per CTA
+constexpr int kColorWarps = 4;     // warps per CTA
 constexpr int kBins = 256;
 constexpr float kMagicC = 12582912.0f;
 constexpr int kMagicBitsC = 0x4B400000;
@@ -113,129 +113,180 @@ __device__ __forceinline__ int select_rank(const unsigned c[8], unsigned before,
   return __shfl_sync(0xffffffffu, found, src);
 }
 
+#ifndef DMI_COLOR_Q
+#define DMI_COLOR_Q 8            // points per warp batch: each lane projects them with ITS view (amortises the view's rows,
+#endif                           // and neighbouring points share image sectors); 3 x 256 x 16-bit bins of shared memory each
+
 // Histograms: 3 channels x 256 bins x 16-bit counters per point, two bins per 32-bit word (shared-memory
-// atomics are 32-bit); requires nViews < 65536, which the launcher checks.
+// atomics are 32-bit); requires nViews < 65536, which the launcher checks.  Sum and count come out of the histogram
+// too (sum = sum_b b * count_b), so the lanes carry no per-point accumulators through the view loop.
+// The view loop runs in three phases per lane-view, so that the Q colour gathers of a lane are in flight together:
+//   1  project the Q points (FP32 tier; uncertified ones through the FP64 / exact tiers afterwards, one call site)
+//   2  gather: the RGB triple = 3 bytes at byte offset 3*idx, fetched as the two aligned 32-bit words around it
+//   3  three shared-memory atomics per hit
 template <typename XYZ, int Q>
-__global__ void __launch_bounds__(32 * kColorWarps, 2)
+__global__ void __launch_bounds__(32 * kColorWarps)
 colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_constant__ ColorViews views,
-                const uint8_t* __restrict__ colors, int W, int H,
+                const uint8_t* __restrict__ colors, size_t colorBytes, int W, int H,
                 uint8_t* __restrict__ mean, uint8_t* __restrict__ median, int32_t* __restrict__ nb)
 {
-  __shared__ unsigned hist[kColorWarps][Q][3][kBins / 2];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // per warp: Q points as float4 (x, y, z, max |coordinate|), then Q x 3 x 128 words of histogram
+  constexpr int kWarpWords = Q * 4 + Q * 3 * (kBins / 2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned* wbase = reinterpret_cast<unsigned*>(smem_raw) + (size_t)warp * kWarpWords;
+  float4* pw = reinterpret_cast<float4*>(wbase);
+  unsigned* hw = wbase + Q * 4;
   const size_t npix = (size_t)W * H;
   const size_t batches = (nPoints + Q - 1) / Q;
   const size_t warpsTotal = (size_t)gridDim.x * kColorWarps;
   const int pxoff = kMagicBitsC - views.cxc, pyoff = kMagicBitsC - views.cyc;
   const float T = views.T;
+  const unsigned* words = reinterpret_cast<const unsigned*>(colors);     // cudaMalloc'ed or 4-byte aligned (checked by the launcher)
+  const size_t lastWord = (colorBytes - 1) >> 2;
 
   for (size_t bt = (size_t)blockIdx.x * kColorWarps + warp; bt < batches; bt += warpsTotal)
   {
     const size_t p0 = bt * Q;
-    unsigned* hw = &hist[warp][0][0][0];
 #pragma unroll
     for (int q = 0; q < Q * 3 * kBins / 2 / 32; q++) hw[q * 32 + lane] = 0u;
-    __syncwarp();
-    // vtkPoints::GetPoint: stored type promoted to double (MeshColoration.cxx:147-148)
-    float xf[Q], yf[Q], zf[Q], mf[Q];
-    bool fexact[Q];
-    unsigned s0[Q], s1[Q], s2[Q], n[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++)
+    // vtkPoints::GetPoint: stored type promoted to double (MeshColoration.cxx:147-148).  T1 needs exact float inputs
+    // and a finite magnitude bound: a point that is not float-representable is marked by a NaN bound (never certified)
+    unsigned inexact = 0;
+    if (lane < Q)
     {
-      const size_t p = min(p0 + q, nPoints - 1);
+      const size_t p = min(p0 + lane, nPoints - 1);
       const double xd = (double)xyz[3 * p + 0], yd = (double)xyz[3 * p + 1], zd = (double)xyz[3 * p + 2];
-      xf[q] = (float)xd; yf[q] = (float)yd; zf[q] = (float)zd;
-      // T1 needs exact float inputs and a finite magnitude bound
-      fexact[q] = (double)xf[q] == xd && (double)yf[q] == yd && (double)zf[q] == zd;
-      mf[q] = fmaxf(fabsf(xf[q]), fmaxf(fabsf(yf[q]), fabsf(zf[q])));
-      s0[q] = s1[q] = s2[q] = n[q] = 0u;
+      const float xf = (float)xd, yf = (float)yd, zf = (float)zd;
+      const bool exact = (double)xf == xd && (double)yf == yd && (double)zf == zd;
+      pw[lane] = make_float4(xf, yf, zf, exact ? fmaxf(fabsf(xf), fmaxf(fabsf(yf), fabsf(zf))) : NAN);
     }
+    __syncwarp();
+    (void)inexact;
     for (int v = lane; v < views.nViews; v += 32)
     {
       // this lane's view, FP32 form: 80 bytes
       const float4* fp = reinterpret_cast<const float4*>(views.fast + v);
       const float4 rx = __ldg(fp + 0), ry = __ldg(fp + 1), rz = __ldg(fp + 2), pe = __ldg(fp + 3), pz = __ldg(fp + 4);
-      const uint8_t* img = colors + npix * 3 * (size_t)v;
+      const size_t vbase = npix * 3 * (size_t)v;
+      // ---- phase 1: pixel of each point in this view, or -1
+      int idx[Q];
+      unsigned slow = 0;
 #pragma unroll
       for (int q = 0; q < Q; q++)
       {
-        const float fz = fmaf(xf[q], rz.x, fmaf(yf[q], rz.y, fmaf(zf[q], rz.z, rz.w)));
-        const float fx = fmaf(xf[q], rx.x, fmaf(yf[q], rx.y, fmaf(zf[q], rx.z, rx.w)));
-        const float fy = fmaf(xf[q], ry.x, fmaf(yf[q], ry.y, fmaf(zf[q], ry.z, ry.w)));
+        const float4 P = pw[q];                                     // broadcast
+        const float fz = fmaf(P.x, rz.x, fmaf(P.y, rz.y, fmaf(P.z, rz.z, rz.w)));
+        const float fx = fmaf(P.x, rx.x, fmaf(P.y, rx.y, fmaf(P.z, rx.z, rx.w)));
+        const float fy = fmaf(P.x, ry.x, fmaf(P.y, ry.y, fmaf(P.z, ry.z, ry.w)));
         const float r = rcp_approx_c(fz), ar = fabsf(r);
         const float tu = fmaf(fx, r, kMagicC), tv = fmaf(fy, r, kMagicC);
         const float pu = tu - kMagicC, pv = tv - kMagicC;
         const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);
-        const float Ex = fmaf(pe.x, mf[q], pe.y), Ey = fmaf(pe.z, mf[q], pe.w), zm = fmaf(pz.x, mf[q], pz.y);
+        const float Ex = fmaf(pe.x, P.w, pe.y), Ey = fmaf(pe.z, P.w, pe.w), zm = fmaf(pz.x, P.w, pz.y);
         const float tx = fmaf(-Ex, ar, T), ty = fmaf(-Ey, ar, T);
-        const bool cert = fexact[q] && (fabsf(fz) > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
+        // a NaN bound (inexact point) or a NaN projection fails every compare
+        const bool cert = (fabsf(fz) > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
         const int px = __float_as_int(tu) - pxoff, py = __float_as_int(tv) - pyoff;
-        int idx = (cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H) ? (H - 1 - py) * W + px : -1;
-        if (!cert)
-          idx = project_slow<XYZ>(views, v, xyz, min(p0 + q, nPoints - 1), mf[q], fexact[q] ? pu : NAN, fexact[q] ? pv : NAN, W, H);
-        if (idx >= 0)
+        idx[q] = (cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H) ? (H - 1 - py) * W + px : -1;
+        if (!cert) slow |= 1u << q;
+      }
+      // ---- uncertified (point, view) pairs: FP64 tier, then the reference's own operation sequence; dynamic q
+      while (slow)
+      {
+        const int q = __ffs(slow) - 1;
+        slow &= slow - 1;
+        const float4 P = pw[q];
+        const bool exact = P.w == P.w;
+        float pu = NAN, pv = NAN;
+        if (exact)
         {
-          const uint8_t* c = img + (size_t)idx * 3;
-          const unsigned cr = c[0], cg = c[1], cb = c[2];
-          atomicAdd(&hist[warp][q][0][cr >> 1], 1u << ((cr & 1) * 16));
-          atomicAdd(&hist[warp][q][1][cg >> 1], 1u << ((cg & 1) * 16));
-          atomicAdd(&hist[warp][q][2][cb >> 1], 1u << ((cb & 1) * 16));
-          s0[q] += cr; s1[q] += cg; s2[q] += cb; n[q]++;
+          const float fz = fmaf(P.x, rz.x, fmaf(P.y, rz.y, fmaf(P.z, rz.z, rz.w)));
+          const float r = rcp_approx_c(fz);
+          pu = fmaf(fmaf(P.x, rx.x, fmaf(P.y, rx.y, fmaf(P.z, rx.z, rx.w))), r, kMagicC) - kMagicC;
+          pv = fmaf(fmaf(P.x, ry.x, fmaf(P.y, ry.y, fmaf(P.z, ry.z, ry.w))), r, kMagicC) - kMagicC;
+        }
+        const size_t p = min(p0 + q, nPoints - 1);
+        float mf = P.w;
+        if (!exact)
+        {
+          const double xd = (double)xyz[3 * p + 0], yd = (double)xyz[3 * p + 1], zd = (double)xyz[3 * p + 2];
+          mf = fmaxf(fabsf((float)xd), fmaxf(fabsf((float)yd), fabsf((float)zd)));
+        }
+        const int id = project_slow<XYZ>(views, v, xyz, p, mf, pu, pv, W, H);
+#pragma unroll
+        for (int qq = 0; qq < Q; qq++) if (qq == q) idx[qq] = id;
+      }
+      // ---- phase 2: gathers, all in flight together.  Bytes 3*idx .. 3*idx + 2 of the view = GetColorValue's tuple
+      // (ReconstructionData.cxx:107-115), taken from the two aligned words that hold them.
+      unsigned w0[Q], w1[Q];
+#pragma unroll
+      for (int q = 0; q < Q; q++)
+      {
+        const size_t o = vbase + (size_t)(idx[q] < 0 ? 0 : idx[q]) * 3;
+        const size_t a = o >> 2;
+        w0[q] = __ldg(words + a);
+        w1[q] = __ldg(words + min(a + 1, lastWord));                // the clamp only bites on the buffer's very last word,
+      }                                                             // whose triple never reaches into a following word
+      // ---- phase 3: histograms
+#pragma unroll
+      for (int q = 0; q < Q; q++)
+      {
+        if (idx[q] >= 0)
+        {
+          const unsigned sh = (unsigned)((vbase + (size_t)idx[q] * 3) & 3) * 8;
+          const unsigned rgb = __funnelshift_r(w0[q], w1[q], sh);
+          const unsigned cr = rgb & 0xffu, cg = (rgb >> 8) & 0xffu, cb = (rgb >> 16) & 0xffu;
+          unsigned* h = hw + q * 3 * (kBins / 2);
+          atomicAdd(h + (cr >> 1), 1u << ((cr & 1) * 16));
+          atomicAdd(h + (kBins / 2) + (cg >> 1), 1u << ((cg & 1) * 16));
+          atomicAdd(h + kBins + (cb >> 1), 1u << ((cb & 1) * 16));
         }
       }
     }
     __syncwarp();
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < Q; q++)
     {
-      unsigned a0 = s0[q], a1 = s1[q], a2 = s2[q], an = n[q];
+      unsigned med[3] = {0u, 0u, 0u}, avg[3] = {0u, 0u, 0u}, an = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int ch = 0; ch < 3; ch++)
       {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        an += __shfl_xor_sync(0xffffffffu, an, o);
-      }
-      unsigned med[3] = {0u, 0u, 0u};
-      if (an > 0)
-      {
-        const unsigned hiRank = an / 2, loRank = (an % 2 == 0) ? an / 2 - 1 : an / 2;
+        unsigned c[8], tot = 0, wsum = 0;
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++)
+        for (int k = 0; k < 4; k++)
         {
-          unsigned c[8], tot = 0;
+          const unsigned wv = hw[(q * 3 + ch) * (kBins / 2) + lane * 4 + k];
+          c[2 * k] = wv & 0xffffu; c[2 * k + 1] = wv >> 16;
+          tot += c[2 * k] + c[2 * k + 1];
+          wsum += c[2 * k] * (unsigned)(lane * 8 + 2 * k) + c[2 * k + 1] * (unsigned)(lane * 8 + 2 * k + 1);
+        }
+        unsigned incl = tot;
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-          {
-            const unsigned wv = hist[warp][q][ch][lane * 4 + k];
-            c[2 * k] = wv & 0xffffu; c[2 * k + 1] = wv >> 16;
-            tot += c[2 * k] + c[2 * k + 1];
-          }
-          unsigned incl = tot;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1)
-          {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-          }
+        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        an = __shfl_sync(0xffffffffu, incl, 31);                  // the same for the three channels
+        if (an > 0)
+        {
+          const unsigned hiRank = an / 2, loRank = (an % 2 == 0) ? an / 2 - 1 : an / 2;
           const unsigned before = incl - tot;
           const int a = select_rank(c, before, hiRank, lane);
           const int b = select_rank(c, before, loRank, lane);
-          med[ch] = (unsigned)(a + b) >> 1;      // odd n: a == b
+          med[ch] = (unsigned)(a + b) >> 1;                         // odd n: a == b
+          avg[ch] = wsum / an;                                       // int sum / n, truncated (MeshColoration.cxx:176-180)
         }
       }
       const size_t p = p0 + q;
       if (lane == 0 && p < nPoints)
       {
         // n == 0: arrays keep their zero fill (MeshColoration.cxx:116-118,124-126,132)
-        mean[3 * p + 0] = an ? (uint8_t)(a0 / an) : 0;
-        mean[3 * p + 1] = an ? (uint8_t)(a1 / an) : 0;
-        mean[3 * p + 2] = an ? (uint8_t)(a2 / an) : 0;
-        median[3 * p + 0] = (uint8_t)med[0];
-        median[3 * p + 1] = (uint8_t)med[1];
-        median[3 * p + 2] = (uint8_t)med[2];
+        mean[3 * p + 0] = (uint8_t)avg[0]; mean[3 * p + 1] = (uint8_t)avg[1]; mean[3 * p + 2] = (uint8_t)avg[2];
+        median[3 * p + 0] = (uint8_t)med[0]; median[3 * p + 1] = (uint8_t)med[1]; median[3 * p + 2] = (uint8_t)med[2];
         nb[p] = (int32_t)an;
       }
     }
@@ -249,16 +300,31 @@ cudaError_t launch_colorize(size_t nPoints, const void* d_xyz, int xyzType, Colo
 {
   if (nPoints == 0) return cudaSuccess;
   if (views.nViews >= 65536) return cudaErrorInvalidValue;   // 16-bit histogram counters
-  constexpr int Q = 4;
+  if (reinterpret_cast<uintptr_t>(d_colors) & 3) return cudaErrorMisalignedAddress;
+  constexpr int Q = DMI_COLOR_Q;
+  constexpr size_t smem = (size_t)kColorWarps * (Q * 4 + Q * 3 * (kBins / 2)) * 4;
+  const size_t colorBytes = (size_t)views.nViews * W * H * 3;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t perSm = std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
   size_t blocks = ((nPoints + Q - 1) / Q + kColorWarps - 1) / kColorWarps;
-  const size_t cap = 148 * 8;                       // persistent: CTAs stride over the point batches
-  if (blocks > cap) blocks = cap;
+  blocks = std::min(blocks, (size_t)sms * perSm);            // persistent: CTAs stride over the point batches
+  cudaError_t e;
   if (xyzType == 1)
-    colorize_kernel<double, Q><<<(unsigned)blocks, 32 * kColorWarps, 0, s>>>(
-        nPoints, (const double*)d_xyz, views, d_colors, W, H, d_mean, d_median, d_nb);
+  {
+    e = cudaFuncSetAttribute(colorize_kernel<double, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    colorize_kernel<double, Q><<<(unsigned)blocks, 32 * kColorWarps, smem, s>>>(
+        nPoints, (const double*)d_xyz, views, d_colors, colorBytes, W, H, d_mean, d_median, d_nb);
+  }
   else
-    colorize_kernel<float, Q><<<(unsigned)blocks, 32 * kColorWarps, 0, s>>>(
-        nPoints, (const float*)d_xyz, views, d_colors, W, H, d_mean, d_median, d_nb);
+  {
+    e = cudaFuncSetAttribute(colorize_kernel<float, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    colorize_kernel<float, Q><<<(unsigned)blocks, 32 * kColorWarps, smem, s>>>(
+        nPoints, (const float*)d_xyz, views, d_colors, colorBytes, W, H, d_mean, d_median, d_nb);
+  }
   return cudaGetLastError();
 }
 
