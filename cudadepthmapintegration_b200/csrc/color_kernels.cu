@@ -13,9 +13,11 @@
 // Which pixel a point falls on (ReconstructionData::TransformWorldToDepthMapPosition, ~37 uncontracted
 // FP64 operations + 2 IEEE divisions in the reference) is decided by the same three certified tiers as
 // the integration kernel (DESIGN.md "certification"):
-//   T1  FP32: composed 3x4 rows (9 FFMA), MUFU.RCP, magic-number rounding, distance to the integer
-//       against 0.5 - (E*|r| + c0) with E = kE * (A*m + B) from per-view coefficient sums and the
-//       point's max |coordinate| m.  Mesh points are float32 (vtkPoints' default), hence exact inputs.
+//   T1  FP32: the composed rows are evaluated in FP64 at the batch's FIRST point (per lane-view, amortised over the
+//       batch) and rounded to float; each point adds its float offset from that point through the float coefficients
+//       (like the integration kernel's brick bases: the large, cancelling terms stay in FP64, the FP32 error scales with
+//       the small local terms).  MUFU.RCP, magic-number rounding, distance to the integer against 0.5 - (E*|r| + c0),
+//       E = kE * ((|b_n| + A_n d) + U1 (|b_z| + A_z d)).  Mesh points are float32 (vtkPoints' default), hence exact inputs.
 //   T2  FP64 composed rows + residual test of the candidate (margin 2^-44 of the magnitudes the
 //       reference's own evaluation order goes through).
 //   T3  the reference's operation sequence (project_exact), on ties / near-zero denominators / double
@@ -67,12 +69,10 @@ __device__ __noinline__ int project_exact(const double* __restrict__ m, int stri
 }
 
 // T2, falling through to T3.  pu, pv: T1's candidate (centred integer pixel as float), or NaN for "none".
-template <typename XYZ>
-__device__ __noinline__ int project_slow(const ColorViews& views, int v, const XYZ* __restrict__ xyz, size_t p, float mf,
+__device__ __noinline__ int project_slow(const ColorViews& views, int v, double x, double y, double z, float mf,
                                          float pu, float pv, int W, int H)
 {
-  // the point is re-read here so that the hot loop keeps only its float copy in registers
-  const double x = (double)xyz[3 * p + 0], y = (double)xyz[3 * p + 1], z = (double)xyz[3 * p + 2], m = (double)mf;
+  const double m = (double)mf;
   const ColorViewT2& V = views.t2[v];
   const double dz = fma(x, V.dz[0], fma(y, V.dz[1], fma(z, V.dz[2], V.dz[3])));
   const double adz = fabs(dz);
@@ -114,7 +114,7 @@ __device__ __forceinline__ int select_rank(const unsigned c[8], unsigned before,
 }
 
 #ifndef DMI_COLOR_Q
-#define DMI_COLOR_Q 8            // points per warp batch: each lane projects them with ITS view (amortises the view's rows,
+#define DMI_COLOR_Q 16           // points per warp batch: each lane projects them with ITS view (amortises the view's rows,
 #endif                           // and neighbouring points share image sectors); 3 x 256 x 16-bit bins of shared memory each
 
 // Histograms: 3 channels x 256 bins x 16-bit counters per point, two bins per 32-bit word (shared-memory
@@ -131,12 +131,13 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
                 uint8_t* __restrict__ mean, uint8_t* __restrict__ median, int32_t* __restrict__ nb)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // per warp: Q points as float4 (x, y, z, max |coordinate|), then Q x 3 x 128 words of histogram
-  constexpr int kWarpWords = Q * 4 + Q * 3 * (kBins / 2);
+  // per warp: the reference point + the largest offset (4 doubles), Q offsets as float4, then Q x 3 x 128 words of histogram
+  constexpr int kWarpWords = 8 + Q * 4 + Q * 3 * (kBins / 2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned* wbase = reinterpret_cast<unsigned*>(smem_raw) + (size_t)warp * kWarpWords;
-  float4* pw = reinterpret_cast<float4*>(wbase);
-  unsigned* hw = wbase + Q * 4;
+  double* pref = reinterpret_cast<double*>(wbase);
+  float4* pw = reinterpret_cast<float4*>(wbase + 8);
+  unsigned* hw = wbase + 8 + Q * 4;
   const size_t npix = (size_t)W * H;
   const size_t batches = (nPoints + Q - 1) / Q;
   const size_t warpsTotal = (size_t)gridDim.x * kColorWarps;
@@ -150,24 +151,40 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
     const size_t p0 = bt * Q;
 #pragma unroll
     for (int q = 0; q < Q * 3 * kBins / 2 / 32; q++) hw[q * 32 + lane] = 0u;
-    // vtkPoints::GetPoint: stored type promoted to double (MeshColoration.cxx:147-148).  T1 needs exact float inputs
-    // and a finite magnitude bound: a point that is not float-representable is marked by a NaN bound (never certified)
-    unsigned inexact = 0;
-    if (lane < Q)
+    // vtkPoints::GetPoint: stored type promoted to double (MeshColoration.cxx:147-148).  T1 needs exact float inputs:
+    // a point that is not float-representable is marked by a NaN (never certified).  pw[q] = offset of point q from the
+    // batch's first point (x, y, z) and, in w, 1 or that NaN.
     {
-      const size_t p = min(p0 + lane, nPoints - 1);
+      const size_t p = min(p0 + min(lane, Q - 1), nPoints - 1);
       const double xd = (double)xyz[3 * p + 0], yd = (double)xyz[3 * p + 1], zd = (double)xyz[3 * p + 2];
       const float xf = (float)xd, yf = (float)yd, zf = (float)zd;
       const bool exact = (double)xf == xd && (double)yf == yd && (double)zf == zd;
-      pw[lane] = make_float4(xf, yf, zf, exact ? fmaxf(fabsf(xf), fmaxf(fabsf(yf), fabsf(zf))) : NAN);
+      const float x0 = __shfl_sync(0xffffffffu, xf, 0), y0 = __shfl_sync(0xffffffffu, yf, 0), z0 = __shfl_sync(0xffffffffu, zf, 0);
+      const bool ok0 = __shfl_sync(0xffffffffu, exact ? 1 : 0, 0) != 0;
+      const float dx = xf - x0, dy = yf - y0, dz = zf - z0;
+      float d = (exact && ok0) ? fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz))) : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+      if (lane < Q) pw[lane] = make_float4(dx, dy, dz, (exact && ok0) ? 1.f : NAN);
+      if (lane == 0) { pref[0] = (double)x0; pref[1] = (double)y0; pref[2] = (double)z0; pref[3] = (double)d; }
     }
     __syncwarp();
-    (void)inexact;
+    const double rx0 = pref[0], ry0 = pref[1], rz0 = pref[2];
+    const float dmax = (float)pref[3];
     for (int v = lane; v < views.nViews; v += 32)
     {
-      // this lane's view, FP32 form: 80 bytes
+      // this lane's view: the composed rows in double at the reference point -> float bases; float coefficients
+      const double2* tp = reinterpret_cast<const double2*>(views.t2 + v);
+      const double2 n0 = __ldg(tp + 0), n1 = __ldg(tp + 1), m0 = __ldg(tp + 2), m1 = __ldg(tp + 3), z0r = __ldg(tp + 4), z1r = __ldg(tp + 5);
+      const float bx = __double2float_rn(fma(rx0, n0.x, fma(ry0, n0.y, fma(rz0, n1.x, n1.y))));
+      const float by = __double2float_rn(fma(rx0, m0.x, fma(ry0, m0.y, fma(rz0, m1.x, m1.y))));
+      const float bz = __double2float_rn(fma(rx0, z0r.x, fma(ry0, z0r.y, fma(rz0, z1r.x, z1r.y))));
       const float4* fp = reinterpret_cast<const float4*>(views.fast + v);
-      const float4 rx = __ldg(fp + 0), ry = __ldg(fp + 1), rz = __ldg(fp + 2), pe = __ldg(fp + 3), pz = __ldg(fp + 4);
+      const float4 rx = __ldg(fp + 0), ry = __ldg(fp + 1), rz = __ldg(fp + 2);
+      const float lz = fmaf(rz.w, dmax, fabsf(bz));
+      const float Ex = views.kE * (fmaf(rx.w, dmax, fabsf(bx)) + views.U1 * lz);
+      const float Ey = views.kE * (fmaf(ry.w, dmax, fabsf(by)) + views.U1 * lz);
+      const float zm = views.kZ * lz;
       const size_t vbase = npix * 3 * (size_t)v;
       // ---- phase 1: pixel of each point in this view, or -1
       int idx[Q];
@@ -176,16 +193,15 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
       for (int q = 0; q < Q; q++)
       {
         const float4 P = pw[q];                                     // broadcast
-        const float fz = fmaf(P.x, rz.x, fmaf(P.y, rz.y, fmaf(P.z, rz.z, rz.w)));
-        const float fx = fmaf(P.x, rx.x, fmaf(P.y, rx.y, fmaf(P.z, rx.z, rx.w)));
-        const float fy = fmaf(P.x, ry.x, fmaf(P.y, ry.y, fmaf(P.z, ry.z, ry.w)));
+        const float fz = bz + fmaf(P.x, rz.x, fmaf(P.y, rz.y, P.z * rz.z));
+        const float fx = bx + fmaf(P.x, rx.x, fmaf(P.y, rx.y, P.z * rx.z));
+        const float fy = by + fmaf(P.x, ry.x, fmaf(P.y, ry.y, P.z * ry.z));
         const float r = rcp_approx_c(fz), ar = fabsf(r);
         const float tu = fmaf(fx, r, kMagicC), tv = fmaf(fy, r, kMagicC);
         const float pu = tu - kMagicC, pv = tv - kMagicC;
         const float eu = fmaf(fx, r, -pu), ev = fmaf(fy, r, -pv);
-        const float Ex = fmaf(pe.x, P.w, pe.y), Ey = fmaf(pe.z, P.w, pe.w), zm = fmaf(pz.x, P.w, pz.y);
-        const float tx = fmaf(-Ex, ar, T), ty = fmaf(-Ey, ar, T);
-        // a NaN bound (inexact point) or a NaN projection fails every compare
+        const float tx = fmaf(-Ex, ar, T) * P.w, ty = fmaf(-Ey, ar, T);      // P.w = 1, or NaN for an inexact point
+        // a NaN threshold (inexact point) or a NaN projection fails every compare
         const bool cert = (fabsf(fz) > zm) && (fabsf(eu) < tx) && (fabsf(ev) < ty);
         const int px = __float_as_int(tu) - pxoff, py = __float_as_int(tv) - pyoff;
         idx[q] = (cert && (unsigned)px < (unsigned)W && (unsigned)py < (unsigned)H) ? (H - 1 - py) * W + px : -1;
@@ -198,22 +214,19 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
         slow &= slow - 1;
         const float4 P = pw[q];
         const bool exact = P.w == P.w;
+        const size_t p = min(p0 + q, nPoints - 1);
+        // the point as the reference sees it (a float point converts exactly)
+        const double x = (double)xyz[3 * p + 0], y = (double)xyz[3 * p + 1], z = (double)xyz[3 * p + 2];
         float pu = NAN, pv = NAN;
         if (exact)
         {
-          const float fz = fmaf(P.x, rz.x, fmaf(P.y, rz.y, fmaf(P.z, rz.z, rz.w)));
+          const float fz = bz + fmaf(P.x, rz.x, fmaf(P.y, rz.y, P.z * rz.z));
           const float r = rcp_approx_c(fz);
-          pu = fmaf(fmaf(P.x, rx.x, fmaf(P.y, rx.y, fmaf(P.z, rx.z, rx.w))), r, kMagicC) - kMagicC;
-          pv = fmaf(fmaf(P.x, ry.x, fmaf(P.y, ry.y, fmaf(P.z, ry.z, ry.w))), r, kMagicC) - kMagicC;
+          pu = fmaf(bx + fmaf(P.x, rx.x, fmaf(P.y, rx.y, P.z * rx.z)), r, kMagicC) - kMagicC;
+          pv = fmaf(by + fmaf(P.x, ry.x, fmaf(P.y, ry.y, P.z * ry.z)), r, kMagicC) - kMagicC;
         }
-        const size_t p = min(p0 + q, nPoints - 1);
-        float mf = P.w;
-        if (!exact)
-        {
-          const double xd = (double)xyz[3 * p + 0], yd = (double)xyz[3 * p + 1], zd = (double)xyz[3 * p + 2];
-          mf = fmaxf(fabsf((float)xd), fmaxf(fabsf((float)yd), fabsf((float)zd)));
-        }
-        const int id = project_slow<XYZ>(views, v, xyz, p, mf, pu, pv, W, H);
+        const float mf = fmaxf(fabsf((float)x), fmaxf(fabsf((float)y), fabsf((float)z)));
+        const int id = project_slow(views, v, x, y, z, mf, pu, pv, W, H);
 #pragma unroll
         for (int qq = 0; qq < Q; qq++) if (qq == q) idx[qq] = id;
       }
@@ -302,7 +315,7 @@ cudaError_t launch_colorize(size_t nPoints, const void* d_xyz, int xyzType, Colo
   if (views.nViews >= 65536) return cudaErrorInvalidValue;   // 16-bit histogram counters
   if (reinterpret_cast<uintptr_t>(d_colors) & 3) return cudaErrorMisalignedAddress;
   constexpr int Q = DMI_COLOR_Q;
-  constexpr size_t smem = (size_t)kColorWarps * (Q * 4 + Q * 3 * (kBins / 2)) * 4;
+  constexpr size_t smem = (size_t)kColorWarps * (8 + Q * 4 + Q * 3 * (kBins / 2)) * 4;
   const size_t colorBytes = (size_t)views.nViews * W * H * 3;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -335,6 +348,19 @@ static float upf(double x)
   float f = (float)x;
   if ((double)f < x) f = nextafterf(f, INFINITY);
   return f;
+}
+
+static float upf(double x);
+
+// FP32 tier of the coloration: f = fl(fl(b) + local), b = the row at the batch's reference point evaluated in double,
+// local = three float FMAs over the offsets (|offset| <= d).  |f - true| <= 7 * 2^-24 * (|b| + A d): one rounding of the base,
+// one of the final add, one of each offset (a difference of floats), three FMA roundings and the coefficient roundings,
+// with 1 % of slack.  E = (4/3) (delta_n + U1 delta_z); |fz| > zm must imply delta_z / |fz| <= 1/4.
+void color_bound_constants(int W, int H, float* kE, float* kZ, float* U1)
+{
+  *kE = upf((4.0 / 3.0) * 7.0 * 1.01 * std::ldexp(1.0, -24));
+  *kZ = upf(4.0 * 7.0 * 1.01 * std::ldexp(1.0, -24));
+  *U1 = upf(std::max(W, H) / 2.0 + 2.0);
 }
 
 float color_threshold_T(int W, int H)
@@ -371,17 +397,11 @@ void compose_color_view(const double* K16, const double* RT16, int cxc, int cyc,
   for (int r = 0; r < 2; r++)
     for (int j = 0; j < 4; j++) rows[r][j] = (double)(D[r][j] - cc[r] * D[2][j]);
   for (int j = 0; j < 4; j++) t2->dz[j] = (double)D[2][j];
-  for (int j = 0; j < 4; j++) { fo->nx[j] = (float)t2->nx[j]; fo->ny[j] = (float)t2->ny[j]; fo->dz[j] = (float)t2->dz[j]; }
   auto A = [](const double* r) { return std::fabs(r[0]) + std::fabs(r[1]) + std::fabs(r[2]); };
+  for (int j = 0; j < 3; j++) { fo->nx[j] = (float)t2->nx[j]; fo->ny[j] = (float)t2->ny[j]; fo->dz[j] = (float)t2->dz[j]; }
+  // [3]: sum of the |coefficients|, rounded up (bounds the local terms A * d of the FP32 tier)
+  fo->nx[3] = upf(A(t2->nx) * (1.0 + 1e-6)); fo->ny[3] = upf(A(t2->ny) * (1.0 + 1e-6)); fo->dz[3] = upf(A(t2->dz) * (1.0 + 1e-6));
   const double U1 = std::max(W, H) / 2.0 + 2.0;
-  // T1: |f - true| <= 7 * 2^-24 * (A*m + B) per row (4 coefficient roundings + 3 FMA roundings), E = (4/3)*(dn + U1*dz)
-  const double kE = (4.0 / 3.0) * 7.0 * 1.01 * std::ldexp(1.0, -24);
-  fo->pax = upf(kE * (A(t2->nx) + U1 * A(t2->dz))); fo->pbx = upf(kE * (std::fabs(t2->nx[3]) + U1 * std::fabs(t2->dz[3])));
-  fo->pay = upf(kE * (A(t2->ny) + U1 * A(t2->dz))); fo->pby = upf(kE * (std::fabs(t2->ny[3]) + U1 * std::fabs(t2->dz[3])));
-  // |fz| > zm must imply dz_err / |fz| <= 1/4
-  const double kZ = 4.0 * 7.0 * 1.01 * std::ldexp(1.0, -24);
-  fo->zma = upf(kZ * A(t2->dz)); fo->zmb = upf(kZ * std::fabs(t2->dz[3]));
-  fo->pad[0] = fo->pad[1] = 0.f;
   // T2 margins: 2^-44 of the reference's intermediate magnitudes (|K3| * |RT| sums), composed rows included
   const double k2 = std::ldexp(1.0, -44);
   const double Ax = Aabs[0] + std::fabs((double)cxc) * Aabs[2], Bx = Babs[0] + std::fabs((double)cxc) * Babs[2];

@@ -688,6 +688,7 @@ static int pack_color_views(dmi_ctx* ctx, int nViews, const double* K, const dou
   out->cxc = cxc;
   out->cyc = cyc;
   out->T = dmi::color_threshold_T(W, H);
+  dmi::color_bound_constants(W, H, &out->kE, &out->kZ, &out->U1);
   return DMI_OK;
 }
 

@@ -138,11 +138,9 @@ cudaError_t launch_depth_threshold(double* d_depths, const double* d_cost, size_
                                    cudaStream_t s);
 
 // coloration
-struct alignas(16) ColorViewFast   // T1 form of one view: rows over (x, y, z, 1), float
+struct alignas(16) ColorViewFast   // T1 form of one view: coefficients of the rows over (x, y, z), float
 {
-  float nx[4], ny[4], dz[4];
-  float pax, pbx, pay, pby;        // E_x = pax * m + pbx, E_y = pay * m + pby (m = max |coordinate| of the point)
-  float zma, zmb, pad[2];          // zm = zma * m + zmb
+  float nx[4], ny[4], dz[4];       // [0..2] coefficients; [3] = sum of the |coefficients| (rounded up): bounds the local terms
 };
 struct ColorViewT2                 // T2 form: the same rows in double + margins
 {
@@ -157,9 +155,12 @@ struct ColorViews
   int nViews;
   int stride;                      // padded view count of m
   int cxc, cyc;
-  float T;
+  float T;                         // certified iff |e| < T - E * |r|
+  float kE, kZ, U1;                // E = kE * ((|b_n| + A_n d) + U1 * (|b_z| + A_z d)), zm = kZ * (|b_z| + A_z d); b = the rows at
+                                   // the batch's reference point, d = the batch's largest |coordinate offset| from it
 };
 float color_threshold_T(int W, int H);
+void color_bound_constants(int W, int H, float* kE, float* kZ, float* U1);
 void compose_color_view(const double* K16, const double* RT16, int cxc, int cyc, int W, int H,
                         ColorViewFast* fast, ColorViewT2* t2);
 cudaError_t launch_colorize(size_t nPoints, const void* d_xyz, int xyzType, ColorViews views,

@@ -39,10 +39,11 @@
 #include <algorithm>
 
 #ifndef DMI_FAST_CTAS
-#define DMI_FAST_CTAS 5          // CTAs of the integration kernel per SM (register cap 65536 / (128 * CTAs))
+#define DMI_FAST_CTAS 6          // CTAs of the integration kernel per SM (register cap 65536 / (128 * CTAs)); measured on config 5,
+                                 // ms per step at (CTAs, halves) = (4,2) 233, (5,2) 224, (6,2) 257, (5,1) 223, (6,1) 216
 #endif
 #ifndef DMI_FAST_HALVES
-#define DMI_FAST_HALVES 2        // 2: gathers of 4 voxels in flight while the other 4 are classified; 1: all 8 at once
+#define DMI_FAST_HALVES 1        // 2: gathers of 4 voxels in flight while the other 4 are classified; 1: all 8 at once
 #endif
 
 namespace dmi {
