@@ -126,13 +126,15 @@ __device__ __forceinline__ int select_rank(const unsigned c[8], unsigned before,
 //   3  three shared-memory atomics per hit
 template <typename XYZ, int Q>
 __global__ void __launch_bounds__(32 * kColorWarps)
-colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_constant__ ColorViews views,
-                const uint8_t* __restrict__ colors, size_t colorBytes, int W, int H,
+colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const unsigned* __restrict__ perm,
+                const __grid_constant__ ColorViews views, const uint8_t* __restrict__ colors, size_t colorBytes, int W, int H,
                 uint8_t* __restrict__ mean, uint8_t* __restrict__ median, int32_t* __restrict__ nb)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // per warp: the reference point + the largest offset (4 doubles), Q offsets as float4, then Q x 3 x 128 words of histogram
-  constexpr int kWarpWords = 8 + Q * 4 + Q * 3 * (kBins / 2);
+  // per warp: the reference point + the largest offset (4 doubles), Q offsets as float4, then Q histograms of 3 x 128 words
+  // (+ 1 word of padding each, so that the same bin of different points falls into different banks)
+  constexpr int kHist = 3 * (kBins / 2) + 1;
+  constexpr int kWarpWords = 8 + Q * 4 + Q * kHist;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned* wbase = reinterpret_cast<unsigned*>(smem_raw) + (size_t)warp * kWarpWords;
   double* pref = reinterpret_cast<double*>(wbase);
@@ -149,13 +151,12 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
   for (size_t bt = (size_t)blockIdx.x * kColorWarps + warp; bt < batches; bt += warpsTotal)
   {
     const size_t p0 = bt * Q;
-#pragma unroll
-    for (int q = 0; q < Q * 3 * kBins / 2 / 32; q++) hw[q * 32 + lane] = 0u;
+    for (int q = lane; q < Q * kHist; q += 32) hw[q] = 0u;
     // vtkPoints::GetPoint: stored type promoted to double (MeshColoration.cxx:147-148).  T1 needs exact float inputs:
     // a point that is not float-representable is marked by a NaN (never certified).  pw[q] = offset of point q from the
     // batch's first point (x, y, z) and, in w, 1 or that NaN.
     {
-      const size_t p = min(p0 + min(lane, Q - 1), nPoints - 1);
+      const size_t p = perm[min(p0 + min(lane, Q - 1), nPoints - 1)];       // batches follow the spatially sorted order
       const double xd = (double)xyz[3 * p + 0], yd = (double)xyz[3 * p + 1], zd = (double)xyz[3 * p + 2];
       const float xf = (float)xd, yf = (float)yd, zf = (float)zd;
       const bool exact = (double)xf == xd && (double)yf == yd && (double)zf == zd;
@@ -192,7 +193,9 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
 #pragma unroll
       for (int q = 0; q < Q; q++)
       {
-        const float4 P = pw[q];                                     // broadcast
+        // lane l takes the points in the order l, l + 1, ... (mod Q): at any step the lanes work on different points, so
+        // their histogram updates of phase 3 do not pile up on one point's few bins (a surface point looks alike in all views)
+        const float4 P = pw[(q + lane) & (Q - 1)];
         const float fz = bz + fmaf(P.x, rz.x, fmaf(P.y, rz.y, P.z * rz.z));
         const float fx = bx + fmaf(P.x, rx.x, fmaf(P.y, rx.y, P.z * rx.z));
         const float fy = by + fmaf(P.x, ry.x, fmaf(P.y, ry.y, P.z * ry.z));
@@ -212,9 +215,10 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
       {
         const int q = __ffs(slow) - 1;
         slow &= slow - 1;
-        const float4 P = pw[q];
+        const int qp = (q + lane) & (Q - 1);
+        const float4 P = pw[qp];
         const bool exact = P.w == P.w;
-        const size_t p = min(p0 + q, nPoints - 1);
+        const size_t p = perm[min(p0 + qp, nPoints - 1)];
         // the point as the reference sees it (a float point converts exactly)
         const double x = (double)xyz[3 * p + 0], y = (double)xyz[3 * p + 1], z = (double)xyz[3 * p + 2];
         float pu = NAN, pv = NAN;
@@ -250,7 +254,7 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
           const unsigned sh = (unsigned)((vbase + (size_t)idx[q] * 3) & 3) * 8;
           const unsigned rgb = __funnelshift_r(w0[q], w1[q], sh);
           const unsigned cr = rgb & 0xffu, cg = (rgb >> 8) & 0xffu, cb = (rgb >> 16) & 0xffu;
-          unsigned* h = hw + q * 3 * (kBins / 2);
+          unsigned* h = hw + ((q + lane) & (Q - 1)) * kHist;
           atomicAdd(h + (cr >> 1), 1u << ((cr & 1) * 16));
           atomicAdd(h + (kBins / 2) + (cg >> 1), 1u << ((cg & 1) * 16));
           atomicAdd(h + kBins + (cb >> 1), 1u << ((cb & 1) * 16));
@@ -269,7 +273,7 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
-          const unsigned wv = hw[(q * 3 + ch) * (kBins / 2) + lane * 4 + k];
+          const unsigned wv = hw[q * kHist + ch * (kBins / 2) + lane * 4 + k];
           c[2 * k] = wv & 0xffffu; c[2 * k + 1] = wv >> 16;
           tot += c[2 * k] + c[2 * k + 1];
           wsum += c[2 * k] * (unsigned)(lane * 8 + 2 * k) + c[2 * k + 1] * (unsigned)(lane * 8 + 2 * k + 1);
@@ -294,9 +298,9 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
           avg[ch] = wsum / an;                                       // int sum / n, truncated (MeshColoration.cxx:176-180)
         }
       }
-      const size_t p = p0 + q;
-      if (lane == 0 && p < nPoints)
+      if (lane == 0 && p0 + q < nPoints)
       {
+        const size_t p = perm[p0 + q];
         // n == 0: arrays keep their zero fill (MeshColoration.cxx:116-118,124-126,132)
         mean[3 * p + 0] = (uint8_t)avg[0]; mean[3 * p + 1] = (uint8_t)avg[1]; mean[3 * p + 2] = (uint8_t)avg[2];
         median[3 * p + 0] = (uint8_t)med[0]; median[3 * p + 1] = (uint8_t)med[1]; median[3 * p + 2] = (uint8_t)med[2];
@@ -307,37 +311,200 @@ colorize_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const __grid_consta
   }
 }
 
+// ---- spatial order of the points ------------------------------------------------------------------------------------
+// The reference walks the mesh in file order; every point is independent (MeshColoration.cxx:140-192), so the kernel
+// may take them in any order.  A batch of Q points shares its FP64 reference point and, view by view, neighbouring image
+// sectors, so batches should be spatially compact whatever the file order is (a contour's vertex list alternates
+// between the front and the back of the surface).  Two-level counting sort by the 30-bit Morton code of a 1024^3 lattice over
+// the bounding box: the upper 18 bits (64^3 cells) through global bucket counts, offsets and a scatter; the lower 12 bits
+// inside each cell by one CTA in shared memory.  Consecutive points then form small patches of the surface, which project
+// onto a few image sectors in every view.  Ties and over-full cells are left in arrival order: results do not depend on it.
+constexpr int kSortBits = 6, kSortBuckets = 1 << (3 * kSortBits);
+constexpr int kFineBits = 4, kFineBins = 1 << (3 * kFineBits), kFineCap = 5120;
+
+__device__ __forceinline__ unsigned ordered_bits(float f)      // monotone map float -> unsigned
+{
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned u)
+{
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+template <typename XYZ>
+__global__ void __launch_bounds__(256) color_bbox_kernel(size_t nPoints, const XYZ* __restrict__ xyz, unsigned* __restrict__ bbox)
+{
+  unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < nPoints; p += (size_t)gridDim.x * blockDim.x)
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+      const float f = (float)xyz[3 * p + a];
+      if (fabsf(f) <= 3.0e38f) { const unsigned u = ordered_bits(f); lo[a] = min(lo[a], u); hi[a] = max(hi[a], u); }
+    }
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+  {
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(bbox + a, lo[a]); atomicMax(bbox + 3 + a, hi[a]); }
+  }
+}
+
+// FINE = false: Morton code of the point's 64^3 cell (18 bits); FINE = true: of its position inside the cell (12 bits)
+template <typename XYZ, bool FINE = false>
+__device__ __forceinline__ unsigned color_sort_key(const XYZ* __restrict__ xyz, size_t p, const unsigned* __restrict__ bbox)
+{
+  unsigned key = 0;
+  constexpr int kAll = kSortBits + kFineBits;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+  {
+    const float lo = from_ordered_bits(bbox[a]), hi = from_ordered_bits(bbox[3 + a]);
+    const float f = (float)xyz[3 * p + a];
+    const float t = (f - lo) / fmaxf(hi - lo, 1e-30f) * (float)(1 << kAll);
+    unsigned q = (t == t) ? (unsigned)fminf(fmaxf(t, 0.f), (float)((1 << kAll) - 1)) : 0u;      // NaN / inf -> cell 0
+    q = FINE ? (q & ((1u << kFineBits) - 1u)) : (q >> kFineBits);
+#pragma unroll
+    for (int b = 0; b < (FINE ? kFineBits : kSortBits); b++) key |= ((q >> b) & 1u) << (3 * b + a);
+  }
+  return key;
+}
+
+template <typename XYZ>
+__global__ void __launch_bounds__(256) color_count_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const unsigned* __restrict__ bbox,
+                                                          unsigned* __restrict__ counts)
+{
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < nPoints; p += (size_t)gridDim.x * blockDim.x)
+    atomicAdd(counts + color_sort_key(xyz, p, bbox), 1u);
+}
+
+// exclusive scan of the bucket counts, in place, one block
+__global__ void __launch_bounds__(1024) color_scan_kernel(unsigned* __restrict__ counts)
+{
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned s_base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < kSortBuckets; b0 += 1024)
+  {
+    const unsigned v = counts[b0 + threadIdx.x];
+    unsigned incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    unsigned before = 0;
+    for (int q = 0; q < w; q++) before += s_w[q];
+    const unsigned base = s_base;
+    counts[b0 + threadIdx.x] = base + before + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_base = base + before + incl;
+    __syncthreads();
+  }
+}
+
+template <typename XYZ>
+__global__ void __launch_bounds__(256) color_scatter_kernel(size_t nPoints, const XYZ* __restrict__ xyz, const unsigned* __restrict__ bbox,
+                                                            unsigned* __restrict__ cursor, unsigned* __restrict__ perm)
+{
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < nPoints; p += (size_t)gridDim.x * blockDim.x)
+    perm[atomicAdd(cursor + color_sort_key(xyz, p, bbox), 1u)] = (unsigned)p;
+}
+
+// after the scatter `ends[b]` = end of cell b's range of `perm` (its start = ends[b - 1]): order each cell by the fine key
+template <typename XYZ>
+__global__ void __launch_bounds__(256) color_refine_kernel(const XYZ* __restrict__ xyz, const unsigned* __restrict__ bbox,
+                                                           const unsigned* __restrict__ ends, unsigned* __restrict__ perm)
+{
+  __shared__ unsigned s_idx[kFineCap];
+  __shared__ unsigned short s_key[kFineCap];
+  __shared__ unsigned s_hist[kFineBins];
+  __shared__ unsigned s_w[8];
+  for (int b = blockIdx.x; b < kSortBuckets; b += gridDim.x)
+  {
+    const unsigned start = b ? ends[b - 1] : 0u, n = ends[b] - start;
+    if (n < 2 || n > (unsigned)kFineCap) continue;             // CTA-uniform
+    for (int q = threadIdx.x; q < kFineBins; q += 256) s_hist[q] = 0u;
+    __syncthreads();
+    for (unsigned q = threadIdx.x; q < n; q += 256)
+    {
+      const unsigned p = perm[start + q];
+      const unsigned k = color_sort_key<XYZ, true>(xyz, p, bbox);
+      s_idx[q] = p; s_key[q] = (unsigned short)k;
+      atomicAdd(s_hist + k, 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the 4096 bins: 16 per thread
+    unsigned local[kFineBins / 256], sum = 0;
+#pragma unroll
+    for (int q = 0; q < kFineBins / 256; q++) { local[q] = sum; sum += s_hist[threadIdx.x * (kFineBins / 256) + q]; }
+    unsigned incl = sum;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    unsigned before = 0;
+    for (int q = 0; q < w; q++) before += s_w[q];
+    const unsigned base = before + incl - sum;
+#pragma unroll
+    for (int q = 0; q < kFineBins / 256; q++) s_hist[threadIdx.x * (kFineBins / 256) + q] = base + local[q];
+    __syncthreads();
+    for (unsigned q = threadIdx.x; q < n; q += 256) perm[start + atomicAdd(s_hist + s_key[q], 1u)] = s_idx[q];
+    __syncthreads();
+  }
+}
+
+size_t colorize_scratch_bytes(size_t nPoints) { return (size_t)kSortBuckets * 4 + 64 + nPoints * 4; }
+
+// d_scratch: colorize_scratch_bytes(nPoints) bytes
 cudaError_t launch_colorize(size_t nPoints, const void* d_xyz, int xyzType, ColorViews views,
                             const uint8_t* d_colors, int W, int H, uint8_t* d_mean, uint8_t* d_median,
-                            int32_t* d_nb, cudaStream_t s)
+                            int32_t* d_nb, void* d_scratch, cudaStream_t s)
 {
   if (nPoints == 0) return cudaSuccess;
+  if (nPoints >= (1ull << 32)) return cudaErrorInvalidValue;  // 32-bit point permutation
   if (views.nViews >= 65536) return cudaErrorInvalidValue;   // 16-bit histogram counters
   if (reinterpret_cast<uintptr_t>(d_colors) & 3) return cudaErrorMisalignedAddress;
   constexpr int Q = DMI_COLOR_Q;
-  constexpr size_t smem = (size_t)kColorWarps * (8 + Q * 4 + Q * 3 * (kBins / 2)) * 4;
+  static_assert((Q & (Q - 1)) == 0 && Q <= 32, "Q must be a power of two");
+  constexpr size_t smem = (size_t)kColorWarps * (8 + Q * 4 + Q * (3 * (kBins / 2) + 1)) * 4;
   const size_t colorBytes = (size_t)views.nViews * W * H * 3;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  unsigned* counts = (unsigned*)d_scratch;
+  unsigned* bbox = counts + kSortBuckets;
+  unsigned* perm = bbox + 16;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)kSortBuckets * 4, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(bbox, 0xff, 12, s);                      // lows = 0xffffffff
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(bbox + 3, 0, 12, s);                     // highs = 0
+  if (e != cudaSuccess) return e;
+  const unsigned sblocks = (unsigned)std::min<size_t>((nPoints + 255) / 256, (size_t)sms * 8);
   const size_t perSm = std::max<size_t>(1, (size_t)(227 * 1024) / (smem + 1024));
   size_t blocks = ((nPoints + Q - 1) / Q + kColorWarps - 1) / kColorWarps;
   blocks = std::min(blocks, (size_t)sms * perSm);            // persistent: CTAs stride over the point batches
-  cudaError_t e;
-  if (xyzType == 1)
-  {
-    e = cudaFuncSetAttribute(colorize_kernel<double, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    colorize_kernel<double, Q><<<(unsigned)blocks, 32 * kColorWarps, smem, s>>>(
-        nPoints, (const double*)d_xyz, views, d_colors, colorBytes, W, H, d_mean, d_median, d_nb);
+#define DMI_COLOR_LAUNCH(XYZ)                                                                                          \
+  {                                                                                                                    \
+    const XYZ* x = (const XYZ*)d_xyz;                                                                                  \
+    color_bbox_kernel<XYZ><<<sblocks, 256, 0, s>>>(nPoints, x, bbox);                                                  \
+    color_count_kernel<XYZ><<<sblocks, 256, 0, s>>>(nPoints, x, bbox, counts);                                         \
+    color_scan_kernel<<<1, 1024, 0, s>>>(counts);                                                                      \
+    color_scatter_kernel<XYZ><<<sblocks, 256, 0, s>>>(nPoints, x, bbox, counts, perm);                                 \
+    color_refine_kernel<XYZ><<<(unsigned)sms * 4, 256, 0, s>>>(x, bbox, counts, perm);                                 \
+    e = cudaFuncSetAttribute(colorize_kernel<XYZ, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    if (e != cudaSuccess) return e;                                                                                    \
+    colorize_kernel<XYZ, Q><<<(unsigned)blocks, 32 * kColorWarps, smem, s>>>(nPoints, x, perm, views, d_colors, colorBytes, W, H, \
+                                                                             d_mean, d_median, d_nb);                  \
   }
-  else
-  {
-    e = cudaFuncSetAttribute(colorize_kernel<float, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    colorize_kernel<float, Q><<<(unsigned)blocks, 32 * kColorWarps, smem, s>>>(
-        nPoints, (const float*)d_xyz, views, d_colors, colorBytes, W, H, d_mean, d_median, d_nb);
-  }
+  if (xyzType == 1) DMI_COLOR_LAUNCH(double) else DMI_COLOR_LAUNCH(float)
+#undef DMI_COLOR_LAUNCH
   return cudaGetLastError();
 }
 

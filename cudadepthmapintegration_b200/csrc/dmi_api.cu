@@ -87,7 +87,7 @@ int dmi_destroy(dmi_ctx* ctx)
   ctx->counters.release();
   ctx->cls.release(); ctx->tiles.release(); ctx->viewscratch.release(); ctx->maskscratch.release();
   ctx->c_xyz.release(); ctx->c_colors.release(); ctx->c_mats.release();
-  ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release();
+  ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release(); ctx->c_sort.release();
   ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
   dmi_host::shard_release(ctx);
   dmi_host::contour_release(ctx);
@@ -712,11 +712,12 @@ int dmi_colorize_device(dmi_ctx* ctx, size_t nPoints, const void* d_xyz, int xyz
   if (rc != DMI_OK) return rc;
   EventSpan span = ctx->color_stats.open();
   DMI_CK(cudaEventRecord(span.a, ctx->stream));
-  DMI_CK(dmi::launch_colorize(nPoints, d_xyz, xyzType, views, d_colors, W, H, d_mean, d_median, d_nb, ctx->stream));
+  DMI_CK(ctx->c_sort.ensure(dmi::colorize_scratch_bytes(nPoints)));
+  DMI_CK(dmi::launch_colorize(nPoints, d_xyz, xyzType, views, d_colors, W, H, d_mean, d_median, d_nb, ctx->c_sort.p, ctx->stream));
   DMI_CK(cudaEventRecord(span.b, ctx->stream));
   ctx->color_stats.pending.push_back(span);
   ctx->color_stats.launches++;
-  ctx->total_launches++;
+  ctx->total_launches += 6;                                  // bounding box, bucket counts, scan, scatter, refine, coloration
   return DMI_OK;
 }
 

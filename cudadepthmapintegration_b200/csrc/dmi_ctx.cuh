@@ -77,7 +77,7 @@ struct dmi_ctx
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   bool slot_used[2] = {false, false};
   // coloration scratch
-  DevBuf c_xyz, c_colors, c_mats, c_mean, c_median, c_nb;
+  DevBuf c_xyz, c_colors, c_mats, c_mean, c_median, c_nb, c_sort;
   KernelStats tsdf_stats, color_stats;
   long long opt_kernel = DMI_TSDF_KERNEL_AUTO, opt_chunk = 0;
   long long total_launches = 0;

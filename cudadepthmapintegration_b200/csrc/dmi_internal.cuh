@@ -163,9 +163,10 @@ float color_threshold_T(int W, int H);
 void color_bound_constants(int W, int H, float* kE, float* kZ, float* U1);
 void compose_color_view(const double* K16, const double* RT16, int cxc, int cyc, int W, int H,
                         ColorViewFast* fast, ColorViewT2* t2);
+size_t colorize_scratch_bytes(size_t nPoints);      // d_scratch of launch_colorize: sort buckets + point permutation
 cudaError_t launch_colorize(size_t nPoints, const void* d_xyz, int xyzType, ColorViews views,
                             const uint8_t* d_colors, int W, int H, uint8_t* d_mean, uint8_t* d_median,
-                            int32_t* d_nb, cudaStream_t s);
+                            int32_t* d_nb, void* d_scratch, cudaStream_t s);
 
 // microbenchmarks
 cudaError_t launch_fp_peak(int which, int blocks, int iters, float* d_sink, cudaStream_t s);

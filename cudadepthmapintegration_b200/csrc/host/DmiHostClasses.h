@@ -22,7 +22,7 @@ class CudaReconstructionFilter
 {
 public:
   explicit CudaReconstructionFilter(int device = 0) { if (dmi_create(device, &ctx_) != DMI_OK) std::cerr << dmi_last_error(nullptr) << std::endl; }
-  ~CudaReconstructionFilter() { dmi_destroy(ctx_); }
+  ~CudaReconstructionFilter() { dmi_destroy(ctx_); dmi_group_destroy(group_); }
   CudaReconstructionFilter(const CudaReconstructionFilter&) = delete;
   void operator=(const CudaReconstructionFilter&) = delete;
 
@@ -36,6 +36,17 @@ public:
   void SetFilePathVTI(const std::string& p) { FilePathVTI = p; }
   void SetGridMatrix(const double m[16]) { std::copy(m, m + 16, GridMatrix); }
   double GetExecutionTime() const { return ExecutionTime; }
+  // new (the reference is single-GPU): run on several GPUs of the box; the z-layers of the grid are dealt to them and the
+  // views exchanged over NVLink inside libdmi_b200 (dmi_group_*); the output is bit-identical to one GPU's
+  bool SetDevices(const std::vector<int>& devices)
+  {
+    dmi_group_destroy(group_);
+    group_ = nullptr;
+    if (devices.size() < 2) return true;
+    if (dmi_group_create(devices.data(), (int)devices.size(), &group_) != DMI_OK)
+    { std::cerr << dmi_last_error(nullptr) << std::endl; group_ = nullptr; return false; }
+    return true;
+  }
 
   // stands for SetInputData(vtkImageData*): GetDimensions / GetOrigin / GetSpacing (.cxx:121-126); POINT dims
   void SetInputGrid(const int dims[3], const double origin[3], const double spacing[3])
@@ -87,6 +98,7 @@ private:
     std::string err;
     if (!ReadVti(vtiList[0], img, err)) { std::cerr << err << std::endl; return -1; }
     const int dd[2] = {img.W, img.H};
+    if (group_) return ComputeOnGroup(vtiList, krtdList, dd);
     if (dmi_initialize(ctx_, GridMatrix, Dims, Origin, Spacing, RayPotentialThickness, RayPotentialRho,
                        RayPotentialEta, RayPotentialDelta, dd) != DMI_OK ||
         dmi_volume_begin(ctx_, nullptr, DMI_F64) != DMI_OK)      // Output was just zero-filled: nothing to upload
@@ -123,7 +135,38 @@ private:
     return 0;
   }
 
+  // several GPUs: every view is read first (each GPU then uploads only the views it owns), one call integrates them
+  int ComputeOnGroup(const std::vector<std::string>& vtiList, const std::vector<std::string>& krtdList, const int dd[2])
+  {
+    if (dmi_group_initialize(group_, GridMatrix, Dims, Origin, Spacing, RayPotentialThickness, RayPotentialRho, RayPotentialEta,
+                             RayPotentialDelta, dd) != DMI_OK)
+    { std::cerr << dmi_group_last_error(group_) << std::endl; return -1; }
+    const size_t npix = (size_t)dd[0] * dd[1], n = vtiList.size();
+    std::vector<double> depth, cost, K(16 * n, 0.0), RT(16 * n, 0.0);
+    depth.reserve(n * npix);
+    bool haveCost = true;
+    std::cout << "START CUDA ON " << n << " Depth map" << std::endl;
+    for (size_t v = 0; v < n; v++)
+    {
+      DepthMapImage img;
+      std::string err;
+      if (!ReadVti(vtiList[v], img, err)) { std::cerr << err << std::endl; return -1; }
+      if ((size_t)img.W * img.H != npix) { std::cerr << vtiList[v] << ": depth map size differs from the first one" << std::endl; return -1; }
+      if (!help::ReadKrtdFile(krtdList[v], &K[16 * v], &RT[16 * v])) return -1;
+      depth.insert(depth.end(), img.depths.begin(), img.depths.end());
+      if (img.bestCost.size() == npix) cost.insert(cost.end(), img.bestCost.begin(), img.bestCost.end());
+      else haveCost = false;
+    }
+    if (!haveCost && !cost.empty())
+    { std::cerr << "Error : 'Best Cost Values' present in some depth maps only" << std::endl; return -1; }
+    if (dmi_group_process_depth_maps(group_, (int)n, depth.data(), haveCost ? cost.data() : nullptr, ThresholdBestCost, K.data(),
+                                     RT.data(), Output.data(), DMI_F64) != DMI_OK)
+    { std::cerr << dmi_group_last_error(group_) << std::endl; return -1; }
+    return 0;
+  }
+
   dmi_ctx* ctx_ = nullptr;
+  dmi_group* group_ = nullptr;
   bool hasGrid_ = false;
   int Dims[3] = {0, 0, 0};
   double Origin[3] = {0, 0, 0}, Spacing[3] = {1, 1, 1};
@@ -165,11 +208,21 @@ public:
       views_ = (int)id + 1;
     }
   }
-  ~MeshColoration() { dmi_destroy(ctx_); }
+  ~MeshColoration() { dmi_destroy(ctx_); dmi_group_destroy(group_); }
   MeshColoration(const MeshColoration&) = delete;
   void operator=(const MeshColoration&) = delete;
 
   void SetInput(const std::vector<float>& xyz) { points_ = xyz; hasInput_ = true; }
+  // new: colour on several GPUs (points sharded by index, colour images exchanged over NVLink; dmi_group_colorize)
+  bool SetDevices(const std::vector<int>& devices)
+  {
+    dmi_group_destroy(group_);
+    group_ = nullptr;
+    if (devices.size() < 2) return true;
+    if (dmi_group_create(devices.data(), (int)devices.size(), &group_) != DMI_OK)
+    { std::cerr << dmi_last_error(nullptr) << std::endl; group_ = nullptr; return false; }
+    return true;
+  }
 
   // ProcessColoration (MeshColoration.cxx:98-199)
   bool ProcessColoration()
@@ -181,6 +234,13 @@ public:
     }
     const size_t P = points_.size() / 3;
     MeanColoration.assign(3 * P, 0); MedianColoration.assign(3 * P, 0); NbProjectedDepthMap.assign(P, 0);
+    if (group_)
+    {
+      if (dmi_group_colorize(group_, P, points_.data(), DMI_F32, views_, colors_.data(), K_.data(), RT_.data(), W_, H_,
+                             MeanColoration.data(), MedianColoration.data(), NbProjectedDepthMap.data()) != DMI_OK)
+      { std::cerr << dmi_group_last_error(group_) << std::endl; return false; }
+      return true;
+    }
     if (dmi_colorize(ctx_, P, points_.data(), DMI_F32, views_, colors_.data(), K_.data(), RT_.data(), W_, H_,
                      MeanColoration.data(), MedianColoration.data(), NbProjectedDepthMap.data()) != DMI_OK)
     { std::cerr << dmi_last_error(ctx_) << std::endl; return false; }
@@ -193,6 +253,7 @@ public:
 
 private:
   dmi_ctx* ctx_ = nullptr;
+  dmi_group* group_ = nullptr;
   bool hasInput_ = false;
   int views_ = 0, W_ = 0, H_ = 0;
   std::vector<float> points_;

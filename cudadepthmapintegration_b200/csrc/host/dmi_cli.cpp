@@ -60,6 +60,15 @@ static std::string str(const Args& a, const char* k, const std::string& def)
   return (it == a.end() || it->second.empty()) ? def : it->second[0];
 }
 
+// --gpus N (new; the reference is single-GPU): devices 0 .. N-1
+static std::vector<int> devices(const Args& a)
+{
+  std::vector<int> d;
+  const int n = (int)num(a, "--gpus", 1);
+  for (int q = 0; q < n; q++) d.push_back(q);
+  return d;
+}
+
 static int reconstruction(const Args& a)
 {
   std::vector<double> dimsv, spacing, origin, end, vx, vy, vz;
@@ -87,6 +96,7 @@ static int reconstruction(const Args& a)
   double gm[16] = {vx[0], vx[1], vx[2], 0, vy[0], vy[1], vy[2], 0, vz[0], vz[1], vz[2], 0, 0, 0, 0, 1};   // :345-359
 
   CudaReconstructionFilter f;
+  if (!f.SetDevices(devices(a))) return 1;
   f.SetInputGrid(dims, origin.data(), spacing.data());
   f.SetGridMatrix(gm);
   f.SetFilePathKRTD(folder + "/" + krt);
@@ -123,6 +133,7 @@ static int coloration(const Args& a)
   std::vector<float> xyz(bytes.size() / 12 * 3);
   memcpy(xyz.data(), bytes.data(), xyz.size() * 4);
   MeshColoration mc(xyz, vti, krtd);
+  if (!mc.SetDevices(devices(a))) return 1;
   if (!mc.ProcessColoration()) return 1;
   auto dump = [&](const std::string& suffix, const void* p, size_t n) { std::ofstream o((out + suffix).c_str(), std::ios::binary); o.write((const char*)p, (std::streamsize)n); return (bool)o; };
   if (!dump(".mean.u8", mc.MeanColoration.data(), mc.MeanColoration.size()) || !dump(".median.u8", mc.MedianColoration.data(), mc.MedianColoration.size()) ||

@@ -87,6 +87,32 @@ def test_vti_reader_reports_a_corrupt_block(tmp_path):
     assert r.returncode != 0 and "Depths" in r.stderr
 
 
+def test_readers_on_a_vtk_style_file_assembled_independently():
+    """tests/golden/vtk_style_view.vti was assembled by tests/golden/make_vti_fixture.py from the VTK file-format description
+    (version 0.1, UInt32 headers, vtkZLibDataCompressor, appended base64 with separately encoded block header) without
+    dataset_io's writer: both readers (C++ DmiVti.h through `dmi_cli inspect`, Python dataset_io) must return its arrays."""
+    _need_cli()
+    import importlib.util
+    g = os.path.join(ROOT, "tests", "golden")
+    spec = importlib.util.spec_from_file_location("make_vti_fixture", os.path.join(g, "make_vti_fixture.py"))
+    fx = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fx)
+    depths, cost, color, K, R, T = fx.arrays()
+    d, c, col, Ks, RTs = dataset_io.load_dataset(os.path.join(g, "vtk_style_vtiList.txt"), os.path.join(g, "vtk_style_kList.txt"))
+    assert np.array_equal(d[0], depths) and np.array_equal(c[0], cost) and np.array_equal(col[0], color)
+    K4 = Ks.reshape(-1, 4, 4)[0]; RT4 = RTs.reshape(-1, 4, 4)[0]
+    assert np.array_equal(K4[:3, :3], K) and np.array_equal(RT4[:3, :3], R) and np.array_equal(RT4[:3, 3], T)
+    r = subprocess.run([CLI, "inspect", "--vti", os.path.join(g, "vtk_style_vtiList.txt"), "--krtd", os.path.join(g, "vtk_style_kList.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    t = r.stdout.strip().splitlines()[1].split()
+    assert int(t[3]) == fx.W and int(t[5]) == fx.H
+    assert float(t[7]) == pytest.approx(float(depths.sum()), rel=1e-13) and float(t[9]) == pytest.approx(float(cost.sum()), rel=1e-13)
+    assert int(t[11]) == int(color.astype(np.int64).sum()) and int(t[13]) == int((depths == -1).sum())
+    assert np.array_equal(np.array([float(x) for x in t[15:31]]).reshape(4, 4)[:3, :3], K)
+    assert np.array_equal(np.array([float(x) for x in t[32:48]]).reshape(4, 4)[:3, 3], T)
+
+
 def test_vti_reader_rejects_a_truncated_ascii_array(tmp_path):
     _need_cli()
     s = Scene(8, 1, 40, 30)
@@ -157,3 +183,36 @@ def test_cli_end_to_end_against_oracle(tmp_path, oracle):
     assert np.array_equal(np.fromfile(str(tmp_path / "col.nb.i32"), dtype=np.int32), wnb)
     assert np.array_equal(np.fromfile(str(tmp_path / "col.median.u8"), dtype=np.uint8).reshape(-1, 3), wmed)
     assert np.array_equal(np.fromfile(str(tmp_path / "col.mean.u8"), dtype=np.uint8).reshape(-1, 3), wmean)
+
+
+@pytest.mark.gpu
+def test_cli_on_two_gpus_is_bit_identical(tmp_path):
+    """dmi_cli --gpus 2 (dmihost::CudaReconstructionFilter::SetDevices / MeshColoration::SetDevices over dmi_group_*)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    _need_cli()
+    from cudadepthmapintegration_b200 import synthetic as syn
+    s = Scene((24, 20, 70), 9, 64, 48, depth_noise=0.25)
+    dataset_io.write_dataset(str(tmp_path), s.depths, s.best_cost, s.colors, s.K, s.RT)
+    end = [repr(float(o + n * sp)) for o, sp, n in zip(s.grid.origin, s.grid.spacing, s.grid.point_dims)]
+    vols = []
+    for gpus in (1, 2):
+        out = tmp_path / f"vol{gpus}.mhd"
+        cmd = [CLI, "reconstruction", "--gridDims", *[str(d) for d in s.grid.point_dims], "--gridOrigin", *[repr(float(x)) for x in s.grid.origin],
+               "--gridEnd", *end, "--dataFolder", str(tmp_path), "--rayThick", repr(s.rp.thick), "--rayRho", repr(s.rp.rho),
+               "--rayEta", repr(s.rp.eta), "--rayDelta", repr(s.rp.delta), "--outputGridFilename", str(out), "--gpus", str(gpus)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        vols.append(np.fromfile(str(tmp_path / f"vol{gpus}.raw"), dtype=np.float64))
+    assert np.count_nonzero(vols[0]) > 0 and np.array_equal(vols[0].view(np.uint64), vols[1].view(np.uint64))
+    pts = syn.fibonacci_sphere_points(2500)
+    pts.tofile(str(tmp_path / "pts.f32"))
+    outs = []
+    for gpus in (1, 2):
+        r = subprocess.run([CLI, "coloration", "--input", str(tmp_path / "pts.f32"), "--output", str(tmp_path / f"col{gpus}"),
+                            "--krtd", str(tmp_path / "kList.txt"), "--vti", str(tmp_path / "vtiList.txt"), "--gpus", str(gpus)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append([np.fromfile(str(tmp_path / f"col{gpus}{sfx}"), dtype=np.uint8) for sfx in (".mean.u8", ".median.u8", ".nb.i32")])
+    assert all(np.array_equal(a, b) for a, b in zip(*outs)) and outs[0][2].any()
