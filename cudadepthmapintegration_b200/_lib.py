@@ -86,6 +86,8 @@ _PROTOTYPES = {
     "dmi_shard_initialize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp]),
     "dmi_shard_view_count": (C.c_int, [_i, _i, _i, _pi]),
     "dmi_shard_view_indices": (C.c_int, [_i, _i, _i, _vp]),
+    "dmi_shard_group_count": (C.c_int, [_i, _i, _pi]),
+    "dmi_shard_group_starts": (C.c_int, [_i, _i, _vp]),
     "dmi_shard_integrate_device": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
     "dmi_shard_integrate_host": (C.c_int, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
     "dmi_shard_gather_volume_device": (C.c_int, [_vp, _i, _vp]),

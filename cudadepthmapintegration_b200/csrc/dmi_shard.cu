@@ -114,22 +114,41 @@ void dmi_host::shard_release(dmi_ctx* ctx)
 namespace {
 
 // ---- who owns which view ------------------------------------------------------------------------------------------
-// Views go in groups of G = per * world (per = 128 / world, at least 1): inside a group, rank r owns the contiguous
-// share [g0 + r * pg, g0 + (r + 1) * pg) clipped to the group, pg = per for a full group and ceil(n / world) for the
-// last, shorter one -- so that one in-place all-gather per array assembles the group in list order.
+// Views go in groups of consecutive views; inside a group of n views, rank r owns the contiguous share
+// [g0 + r * pg, g0 + (r + 1) * pg) clipped to the group, pg = ceil(n / world) -- so that one in-place all-gather per array
+// assembles the group in list order.  A full group holds per * world views (per = 128 / world, at least 1); the first
+// groups are shorter (per/4, per/4, per/2 views per rank) so that the integration starts after a short first exchange,
+// and so are the last ones, so that little is left to integrate once the last views have arrived.
 struct ShardPlan
 {
-  int V, world, per, G, nGroups;
+  int V, world, per;
+  std::vector<int> start;                                 // start[g] .. start[g + 1]: views of group g
   ShardPlan(int nViews, int w) : V(nViews), world(w)
   {
     per = std::max(1, 128 / w);
-    G = per * w;
-    nGroups = (V + G - 1) / G;
+    const int G = per * w;
+    std::vector<int> sizes;
+    int left = V;
+    auto take = [&](int n) { n = std::min(n, left); if (n > 0) { sizes.push_back(n); left -= n; } };
+    if (w > 1 && V >= 3 * G)
+    {
+      const int q = std::max(1, per / 4) * w, h = std::max(1, per / 2) * w;
+      take(q); take(q); take(h);
+      while (left > 2 * q + h + G) take(G);
+      // what is left: up to one more full group's worth, then the short tail
+      const int tail = 2 * q + h;
+      if (left > tail) take(left - tail);
+      take(h); take(q); take(q);
+    }
+    while (left > 0) take(G);
+    start.push_back(0);
+    for (int n : sizes) start.push_back(start.back() + n);
   }
+  int nGroups() const { return (int)start.size() - 1; }
   void group(int g, int& g0, int& g1, int& pg) const
   {
-    g0 = g * G; g1 = std::min(V, g0 + G);
-    pg = (g1 - g0 == G) ? per : (g1 - g0 + world - 1) / world;
+    g0 = start[g]; g1 = start[g + 1];
+    pg = (g1 - g0 + world - 1) / world;
   }
   void share(int g, int rank, int& a, int& b) const      // rank's views of group g: [a, b)
   {
@@ -138,8 +157,8 @@ struct ShardPlan
     a = std::min(g1, g0 + rank * pg);
     b = std::min(g1, a + pg);
   }
-  int count(int rank) const { int n = 0; for (int g = 0; g < nGroups; g++) { int a, b; share(g, rank, a, b); n += b - a; } return n; }
-  int capacity() const { return (per + 1) * world; }    // views a group buffer must hold (padding of the last group included)
+  int count(int rank) const { int n = 0; for (int g = 0; g < nGroups(); g++) { int a, b; share(g, rank, a, b); n += b - a; } return n; }
+  int capacity() const { return (per + 1) * world; }    // views a group buffer must hold (padding of a ragged group included)
 };
 
 int shard_ensure(dmi_ctx* ctx, const ShardPlan& plan, bool wantLo)
@@ -200,7 +219,7 @@ int shard_integrate(dmi_ctx* ctx, int nViews, const double* depths, const double
   EventSpan span = ctx->tsdf_stats.open();
   bool spanOpen = false;
   size_t done = 0;                                        // views of `mine` consumed so far
-  for (int gi = 0; gi < plan.nGroups; gi++)
+  for (int gi = 0; gi < plan.nGroups(); gi++)
   {
     int g0, g1, pg, a, b;
     plan.group(gi, g0, g1, pg);
@@ -370,12 +389,27 @@ int dmi_shard_view_indices(int nViews, int world, int rank, int* indices)
   if (!indices || nViews < 0 || world < 1 || rank < 0 || rank >= world) return DMI_ERR_INVALID_ARGUMENT;
   const ShardPlan plan(nViews, world);
   int n = 0;
-  for (int g = 0; g < plan.nGroups; g++)
+  for (int g = 0; g < plan.nGroups(); g++)
   {
     int a, b;
     plan.share(g, rank, a, b);
     for (int v = a; v < b; v++) indices[n++] = v;
   }
+  return DMI_OK;
+}
+
+int dmi_shard_group_count(int nViews, int world, int* count)
+{
+  if (!count || nViews < 0 || world < 1) return DMI_ERR_INVALID_ARGUMENT;
+  *count = ShardPlan(nViews, world).nGroups();
+  return DMI_OK;
+}
+
+int dmi_shard_group_starts(int nViews, int world, int* starts)
+{
+  if (!starts || nViews < 0 || world < 1) return DMI_ERR_INVALID_ARGUMENT;
+  const ShardPlan plan(nViews, world);
+  for (size_t g = 0; g < plan.start.size(); g++) starts[g] = plan.start[g];
   return DMI_OK;
 }
 
@@ -632,7 +666,7 @@ int dmi_group_process_depth_maps(dmi_group* grp, int nViews, const double* depth
     DMI_CK(dd.ensure(std::max<size_t>(8, (size_t)mine * npix * 8)));
     if (bestCost) DMI_CK(dc.ensure(std::max<size_t>(8, (size_t)mine * npix * 8)));
     size_t off = 0;
-    for (int gi = 0; gi < plan.nGroups; gi++)
+    for (int gi = 0; gi < plan.nGroups(); gi++)
     {
       int a, b;
       plan.share(gi, r, a, b);

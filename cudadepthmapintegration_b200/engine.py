@@ -352,6 +352,18 @@ def shard_view_indices(n_views: int, world: int, rank: int) -> np.ndarray:
     return out[:n.value].copy()
 
 
+def shard_groups(n_views: int, world: int):
+    """[(g0, g1)] the groups of consecutive views the sharded entry points exchange one after the other."""
+    lib = _lib.load()
+    n = C.c_int()
+    if lib.dmi_shard_group_count(int(n_views), int(world), C.byref(n)) != _lib.DMI_OK:
+        raise ValueError("bad arguments")
+    starts = np.zeros(n.value + 1, dtype=np.int32)
+    if lib.dmi_shard_group_starts(int(n_views), int(world), _ptr(starts)) != _lib.DMI_OK:
+        raise ValueError("bad arguments")
+    return [(int(a), int(b)) for a, b in zip(starts[:-1], starts[1:])]
+
+
 def shard_range(n: int, world: int, rank: int):
     """(first, count) of the contiguous block of n items that `rank` owns (points; colour images)."""
     lib = _lib.load()

@@ -236,7 +236,10 @@ int dmi_contour_device_ptr(dmi_ctx* ctx, const float** d_vertices, const int32_t
  *   dmi_comm_init             ncclCommInitRank on the context's device (collective: every rank calls it)
  *   dmi_shard_initialize      dmi_initialize + this rank's layers
  *   dmi_shard_view_count /    which views this rank must supply ("the files it loads"), in the order expected:
- *   dmi_shard_view_indices    groups of 128 consecutive views, each split evenly over the ranks
+ *   dmi_shard_view_indices    groups of consecutive views (128 in a full group, shorter groups at both ends of the list),
+ *                             each split evenly over the ranks in contiguous shares
+ *   dmi_shard_group_count /   the groups themselves: starts[0 .. count] (starts[count] = nViews); rank r's share of group g
+ *   dmi_shard_group_starts    is [starts[g] + r * pg, starts[g] + (r + 1) * pg) clipped to the group, pg = ceil(size / world)
  *   dmi_volume_begin          as usual, on the rank's layers (packed)
  *   dmi_shard_integrate_*     collective; myDepths / myBestCost hold THIS RANK'S views only, K / RT all views
  *   dmi_shard_gather_volume_device   collective; root receives the whole grid in VTK cell order (device memory)
@@ -256,6 +259,8 @@ int dmi_shard_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gr
                          double rayPotentialDelta, const int depthMapDims[2]);
 int dmi_shard_view_count(int nViews, int world, int rank, int* count);
 int dmi_shard_view_indices(int nViews, int world, int rank, int* indices);
+int dmi_shard_group_count(int nViews, int world, int* count);
+int dmi_shard_group_starts(int nViews, int world, int* starts);
 int dmi_shard_integrate_device(dmi_ctx* ctx, int nViews, const double* d_myDepths, const double* d_myBestCost,
                                double thresholdBestCost, const double* K, const double* RT);
 int dmi_shard_integrate_host(dmi_ctx* ctx, int nViews, const double* myDepths, const double* myBestCost,

@@ -39,17 +39,14 @@ def _worker(rank, world, port, n_views, out_path):
         V = s.n_views
         nz = s.grid.n_cells[2]
         plane = s.grid.n_cells[0] * s.grid.n_cells[1]
-        per = max(1, 128 // world)
-        G = per * world
         # each rank "loads" and filters only the views the library says it owns, in that order
         mine = engine.shard_view_indices(V, world, rank)
         my_views = [torch.from_numpy(orc.apply_depth_threshold(s.depths[v], s.best_cost[v], 0.14).reshape(s.H, s.W)) for v in mine]
         layers = engine.layer_cell_ranges(nz, world, rank)
         vol = np.zeros(s.grid.n_voxels)
         used = 0
-        for g0 in range(0, V, G):
-            g1 = min(V, g0 + G)
-            pg = per if g1 - g0 == G else -(-(g1 - g0) // world)
+        for g0, g1 in engine.shard_groups(V, world):
+            pg = -(-(g1 - g0) // world)
             # the group buffer holds world * pg views; rank r's segment starts r * pg views in (padding at the end of a short group)
             a = min(g1, g0 + rank * pg)
             b = min(g1, a + pg)

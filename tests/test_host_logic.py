@@ -72,24 +72,27 @@ def test_render_is_device_independent_in_its_random_fields():
     assert np.array_equal(c1.numpy()[1:], c2.numpy())
 
 
-@pytest.mark.parametrize("V,world", [(1000, 8), (1000, 2), (1000, 1), (100, 4), (7, 2), (10, 3), (5, 8), (129, 4), (128, 8)])
+@pytest.mark.parametrize("V,world", [(1000, 8), (1000, 2), (1000, 1), (1000, 3), (100, 4), (7, 2), (10, 3), (5, 8), (129, 4), (128, 8), (513, 8)])
 def test_view_ownership_covers_all_views_in_order(V, world):
-    """dmi_shard_view_indices: views go in groups of (128 / world) * world consecutive views; inside a group rank r owns
-    one contiguous share, so that an in-place all-gather assembles the group in list order.  Every view has exactly one
-    owner and owners hold their views in increasing order."""
+    """dmi_shard_group_starts / dmi_shard_view_indices: views go in consecutive groups (at most (128 / world) * world views,
+    shorter ones at both ends of a long list); inside a group rank r owns one contiguous share of ceil(n / world) views, so
+    that an in-place all-gather assembles the group in list order.  Every view has exactly one owner and owners hold their
+    views in increasing order."""
     per = max(1, 128 // world)
-    G = per * world
+    groups = engine.shard_groups(V, world)
+    assert groups[0][0] == 0 and groups[-1][1] == V
+    assert all(a1 == b0 and a1 > a0 for (a0, a1), (b0, b1) in zip(groups, groups[1:]))
+    assert all(g1 - g0 <= (per + 1) * world for g0, g1 in groups)
+    if world > 1 and V >= 3 * per * world:
+        assert groups[0][1] - groups[0][0] < per * world and groups[-1][1] - groups[-1][0] < per * world     # short ends
     owned = [engine.shard_view_indices(V, world, r) for r in range(world)]
-    allv = np.concatenate(owned)
-    assert sorted(allv.tolist()) == list(range(V))
+    assert sorted(np.concatenate(owned).tolist()) == list(range(V))
     for r, mine in enumerate(owned):
         assert list(mine) == sorted(mine)
-        for g0 in range(0, V, G):
-            g1 = min(V, g0 + G)
-            pg = per if g1 - g0 == G else -(-(g1 - g0) // world)
-            in_group = [v for v in mine if g0 <= v < g1]
+        for g0, g1 in groups:
+            pg = -(-(g1 - g0) // world)
             lo = min(g1, g0 + r * pg)
-            assert in_group == list(range(lo, min(g1, lo + pg)))
+            assert [v for v in mine if g0 <= v < g1] == list(range(lo, min(g1, lo + pg)))
 
 
 def test_render_views_do_not_depend_on_the_batch():
