@@ -118,10 +118,12 @@ struct PrepareDst
   float* tiles[kMaxPrepareDst];
 };
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 const PrepareDst& dst, long long clsSpare, cudaStream_t s);
+                                 const PrepareDst& dst, long long clsSpare, cudaStream_t s, bool levels = true);
 // d_lo (may be null): residual image of the lossless split depth = (cls, lo), see split_encode
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 float* d_cls, int* d_lo, long long clsSpare, float* d_tileDmax, cudaStream_t s);
+                                 float* d_cls, int* d_lo, long long clsSpare, float* d_tileDmax, cudaStream_t s, bool levels = true);
+// every level of the tile statistics of views whose classification images were received from another GPU
+cudaError_t launch_tile_stats_from_cls(const float* d_cls, int nViews, int W, int H, float* d_tileStats, cudaStream_t s);
 // d_cls[clsSpare] (an index relative to d_cls) must hold -1.0f: launch_prepare_views(n views) writes it at n*W*H
 // d_depths null: the double depths are rebuilt from (d_cls, d_lo)
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,

@@ -1061,14 +1061,89 @@ __global__ void __launch_bounds__(256) view_flag_kernel(const __grid_constant__ 
     for (int r = 0; r < dst.n; r++) dst.tiles[r][(size_t)blockIdx.x * perView + flagOff] = any ? 1.0f : 0.0f;
 }
 
+// Level 0 of the tile statistics from the CLASSIFICATION image alone (what a rank does for views it received over NVLink:
+// the statistics themselves are not exchanged).  cls = the depth rounded to the nearest float, so the neighbouring floats
+// bound the double from above and below: one ulp looser than the owner's own bounds, still exact tests (the brick tests
+// only ever prove that a view contributes nothing / free space; a looser bound proves it a little less often).
+// One warp per 16 x 16 pixels of storage rows (2 x 2 tiles), each lane 8 consecutive pixels, like prepare_views_kernel.
+__global__ void __launch_bounds__(256)
+tile_stats_from_cls_kernel(const float* __restrict__ cls, int nViews, int W, int H, int TW, int TH, int perView, int badOff,
+                           float* __restrict__ tiles)
+{
+  const int lane = threadIdx.x & 31;
+  const int BW = (TW + 1) / 2, BH = (TH + 1) / 2;
+  const size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t blocksPerView = (size_t)BW * BH;
+  if (blk >= blocksPerView * nViews) return;
+  const int v = (int)(blk / blocksPerView);
+  const int t = (int)(blk % blocksPerView);
+  const int by = t / BW, bx = t % BW;
+  const int row = by * 16 + (lane >> 1), col = bx * 16 + (lane & 1) * 8;
+  float dmax = -INFINITY, dmin = INFINITY, bad = 0.f;
+  if (row < H && col < W)
+  {
+    const float* p = cls + (size_t)v * W * H + (size_t)row * W + col;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (col + q < W)
+      {
+        const float f = __ldg(p + q);
+        if (f == -1.0f) bad = 1.f;                               // invalid after the filter
+        else if (f != f) { dmax = INFINITY; dmin = -INFINITY; bad = 1.f; }      // NaN poisons the tile
+        else
+        {
+          // the double lies within half an ulp of f: the next floats up / down bound it (inf stays inf)
+          const float up = (fabsf(f) <= 3.4e38f) ? __int_as_float(__float_as_int(f) + ((f > 0.f) ? 1 : (f < 0.f ? -1 : 0))) : f;
+          const float dn = (fabsf(f) <= 3.4e38f) ? __int_as_float(__float_as_int(f) + ((f > 0.f) ? -1 : (f < 0.f ? 1 : 0))) : f;
+          dmax = fmaxf(dmax, f == 0.f ? 1.4e-45f : up);
+          dmin = fminf(dmin, f == 0.f ? -1.4e-45f : dn);
+        }
+      }
+  }
+#pragma unroll
+  for (int o = 2; o <= 8; o <<= 1)
+  {
+    dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    bad = fmaxf(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+  }
+  const int tx = bx * 2 + (lane & 1), ty = by * 2 + (lane >> 4);
+  if ((lane & 14) == 0 && tx < TW && ty < TH)
+  {
+    const size_t o = (size_t)v * perView;
+    const int q = ty * TW + tx;
+    reinterpret_cast<float2*>(tiles + o)[q] = make_float2(dmax, dmin);
+    tiles[o + badOff + q] = bad;
+  }
+}
+
+// All levels of the tile statistics of nViews views from their classification images (see tile_stats_from_cls_kernel)
+cudaError_t launch_tile_stats_from_cls(const float* d_cls, int nViews, int W, int H, float* d_tileStats, cudaStream_t s)
+{
+  const TilePyramid p = tile_pyramid_layout(W, H);
+  const size_t blocks2x2 = (size_t)((p.tw + 1) / 2) * ((p.th + 1) / 2) * nViews;
+  if (blocks2x2 == 0) return cudaSuccess;
+  tile_stats_from_cls_kernel<<<(unsigned)((blocks2x2 + 7) / 8), 256, 0, s>>>(d_cls, nViews, W, H, p.tw, p.th, p.perView, p.badOff, d_tileStats);
+  PrepareDst dst = {};
+  dst.n = 1;
+  dst.tiles[0] = d_tileStats;
+  const size_t n = (size_t)p.tw * p.th * nViews;
+  for (int l = 1; l < p.nLevels; l++)
+    tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, nViews, p.perView, p.badOff, p.tw, p.th, l);
+  view_flag_kernel<<<nViews, 256, 0, s>>>(dst, p.perView, p.badOff, p.flagOff, p.tw * p.th);
+  return cudaGetLastError();
+}
+
+// levels: false = only the single pass over the maps (classification / residual images, level 0 of the statistics)
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 const PrepareDst& dst, long long clsSpare, cudaStream_t s)
+                                 const PrepareDst& dst, long long clsSpare, cudaStream_t s, bool levels)
 {
   const TilePyramid p = tile_pyramid_layout(W, H);
   const size_t blocks2x2 = (size_t)((p.tw + 1) / 2) * ((p.th + 1) / 2) * nViews;
   if (blocks2x2 == 0 || dst.n <= 0) return cudaSuccess;
   prepare_views_kernel<<<(unsigned)((blocks2x2 + 7) / 8), 256, 0, s>>>(d_depths, d_cost, thr, nViews, W, H, p.tw, p.th, p.perView,
                                                                        p.badOff, dst, clsSpare);
+  if (!levels) return cudaGetLastError();
   const size_t n = (size_t)p.tw * p.th * nViews;
   for (int l = 1; l < p.nLevels; l++)
     tile_level_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, nViews, p.perView, p.badOff, p.tw, p.th, l);
@@ -1077,13 +1152,13 @@ cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, d
 }
 
 cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, double thr, int nViews, int W, int H,
-                                 float* d_cls, int* d_lo, long long clsSpare, float* d_tileStats, cudaStream_t s)
+                                 float* d_cls, int* d_lo, long long clsSpare, float* d_tileStats, cudaStream_t s, bool levels)
 {
   PrepareDst dst = {};
   dst.n = 1;
   dst.cls[0] = d_cls; dst.lo[0] = d_lo; dst.tiles[0] = d_tileStats;
   dst.aligned = ((reinterpret_cast<uintptr_t>(d_cls) | reinterpret_cast<uintptr_t>(d_lo)) & 31) == 0;
-  return launch_prepare_views(d_depths, d_cost, thr, nViews, W, H, dst, clsSpare, s);
+  return launch_prepare_views(d_depths, d_cost, thr, nViews, W, H, dst, clsSpare, s, levels);
 }
 
 // ---- host side: composition of the per-view affine rows ----------------------------------------
