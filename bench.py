@@ -59,7 +59,6 @@ def parse_args():
     ap.add_argument("--emulate-rank", type=int, nargs=2, metavar=("RANK", "WORLD"), default=None,
                     help="N=1 diagnostic: integrate only the z-layers that RANK of WORLD would own (value counts those pairs)")
     ap.add_argument("--quota", type=int, default=0, help="bricks per CTA of the integration kernel (0: the library's default, 32 at N=1, 8 at N>1)")
-    ap.add_argument("--reserved-sms", type=int, default=-1, help="SMs the integration kernel leaves to the NCCL exchange (-1: the library's default, 0 at N=1, 24 at N>1)")
     ap.add_argument("--breakdown", action="store_true", help="N>1: add the per-rank compute / gather spans of the last step to the line")
     ap.add_argument("--cost-model", default="iid", choices=["iid", "coherent"],
                     help="synthetic best-cost maps: independent per pixel (default, the headline workload) or spatially coherent")
@@ -514,8 +513,6 @@ def main():
             ctx.set_slab_layers(32, args.emulate_rank[0], args.emulate_rank[1])
     if args.quota > 0:
         ctx.set_option(_lib.DMI_OPT_BRICK_QUOTA, args.quota)
-    if args.reserved_sms >= 0:
-        ctx.set_option(_lib.DMI_OPT_RESERVED_SMS, args.reserved_sms)
     slab_cells = ctx.slab_cells
 
     # ---- this rank's views, generated on its GPU (stands for "loaded from the files it owns"): the library says which

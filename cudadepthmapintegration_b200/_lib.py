@@ -28,7 +28,6 @@ DMI_OPT_VIEW_CHUNK = 2
 DMI_OPT_TIER_COUNTERS = 3
 DMI_OPT_CULL = 4
 DMI_OPT_BRICK_QUOTA = 5
-DMI_OPT_RESERVED_SMS = 6
 DMI_UNIQUE_ID_BYTES = 128
 
 

@@ -138,9 +138,6 @@ int dmi_set_option(dmi_ctx* ctx, int option, long long value)
     case DMI_OPT_BRICK_QUOTA:
       DMI_REQUIRE(value >= 1 && value <= (1 << 20), "brick quota must be between 1 and 2^20");
       ctx->opt_quota = (int)value; return DMI_OK;
-    case DMI_OPT_RESERVED_SMS:
-      DMI_REQUIRE(value >= 0 && value <= 128, "reserved SMs must be between 0 and 128");
-      ctx->opt_reserved_sms = (int)value; return DMI_OK;
     case DMI_OPT_TIER_COUNTERS:
       ctx->counters_on = value != 0;
       if (ctx->counters_on)
@@ -397,7 +394,7 @@ int dmi_host::integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_
     DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths ? d_depths + npix * v0 : nullptr, d_lo ? d_lo + npix * v0 : nullptr, d_cls + npix * v0, clsSpare - (long long)(npix * (size_t)v0),
                                  d_tiles + tilesPerView * v0, ctx->opt_cull, (dmi::ViewFast*)ctx->viewscratch.p,
                                  (unsigned*)ctx->maskscratch.p, ctx->vol.p, ctx->vol_type,
-                                 ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr, ctx->opt_quota, ctx->opt_reserved_sms, ctx->stream));
+                                 ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr, ctx->opt_quota, ctx->stream));
     ctx->tsdf_stats.launches++;
     ctx->total_launches += ctx->opt_cull ? 4 : 3;         // view staging, supertile culling, compaction, integration
   }

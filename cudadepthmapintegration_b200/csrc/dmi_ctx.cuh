@@ -86,7 +86,6 @@ struct dmi_ctx
   bool counters_on = false;
   bool opt_cull = true;
   int opt_quota = 32;
-  int opt_reserved_sms = 0;            // SMs the integration kernel leaves to other streams' kernels (the NCCL exchange)
   std::string err;
   dmi_shard_state* shard = nullptr;    // set by dmi_comm_init
   dmi_contour_state* contour = nullptr;

@@ -129,7 +129,7 @@ cudaError_t launch_tile_stats_from_cls(const float* d_cls, int nViews, int W, in
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
                              ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
-                             FastCounters* d_counters, int quota, int reservedSms, cudaStream_t s);
+                             FastCounters* d_counters, int quota, cudaStream_t s);
 size_t tsdf_fast_mask_bytes(const GridParams& g);   // size of d_maskScratch: per supertile a 64-bit view mask + a list entry, + work counters
 void compose_fast_view(const GridParams& g, const double* K16, const double* RT16, int cxc, int cyc, ViewFast* out);
 void fill_fast_chunk_constants(const GridParams& g, FastChunk* c);

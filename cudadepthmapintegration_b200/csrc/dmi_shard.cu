@@ -326,8 +326,8 @@ static int attach_comm(dmi_ctx* ctx, ncclComm_t comm, int rank, int world)
   dmi_shard_state* s = new dmi_shard_state();
   s->comm = comm; s->rank = rank; s->world = world;
   ctx->shard = s;
-  // NCCL's all-gather CTAs need whole SMs (they do not fit beside the integration kernel's): keep some free for them
-  if (world > 1 && ctx->opt_reserved_sms == 0) ctx->opt_reserved_sms = 24;
+  // CTAs of the persistent integration kernel retire sooner, so that the exchange's kernels find a free SM slot quickly
+  if (world > 1 && ctx->opt_quota == 32) ctx->opt_quota = 8;
   int lo = 0, hi = 0;
   DMI_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   // high priority: the exchange's few CTAs must not queue behind the integration kernel's

@@ -792,16 +792,9 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
                  const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
                  long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
                  const int* __restrict__ stlist, int* __restrict__ work, int quota,
-                 T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters, int firstReservedSm)
+                 T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters)
 {
   static_assert(kFastChunk <= 64, "two rounds of 32 candidate views per brick");
-  // SMs kept free for the kernels of another stream (the NCCL all-gather of the next views needs whole SMs: its CTAs do
-  // not fit beside ours): a CTA that lands on one of them leaves at once; the others take all the work
-  {
-    unsigned smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    if ((int)smid >= firstReservedSm) return;
-  }
   __shared__ ViewSm s_view[kColBricks][kFastChunk];
   __shared__ ViewConst s_const[kFastChunk];
   __shared__ int s_cnt[kColBricks];
@@ -851,15 +844,6 @@ __global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant_
 // Enough CTAs to take every work item at `quota` each, at least as many as are resident at once on this device
 static unsigned persistent_grid(const void* kernel, unsigned bricks, unsigned quota)
 {
-  if (quota >= (1u << 24))
-  {
-    // no retirement: exactly the resident capacity (the CTAs that land on reserved SMs leave at once)
-    int dev0 = 0, sms0 = 0, per0 = 0;
-    cudaGetDevice(&dev0);
-    cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per0, kernel, FT, 0);
-    return (unsigned)(std::max(sms0, 1) * std::max(per0, 1));
-  }
   int dev = 0, sms = 0, perSm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -872,18 +856,8 @@ template <typename T, bool PINHOLE>
 static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                            const float* d_cls, const float* d_tileDmax, const TilePyramid& pyr, bool cull,
                            long long clsSpare, const ViewFast* d_views, unsigned* d_masks, T* d_vol, int nbi, int nbj,
-                           int nbk, FastCounters* d_counters, int quota, int reservedSms, cudaStream_t s)
+                           int nbk, FastCounters* d_counters, int quota, cudaStream_t s)
 {
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int firstReservedSm = sms;
-  if (reservedSms > 0)
-  {
-    // with SMs set aside nothing needs to squeeze in between our CTAs: they stay until the work is done
-    firstReservedSm = std::max(1, sms - reservedSms);
-    quota = 1 << 28;
-  }
   const int nst = (int)(grid / (FSI * FSJ * FSK));
   grid /= kColBricks;                                         // work items = supertile columns of FSK bricks
   quota = std::max(1, quota / kColBricks);
@@ -895,7 +869,7 @@ static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& 
   compact_supertiles_kernel<<<1, 1024, 0, s>>>(d_masks, nst, cull ? 1 : 0, list, work);
 #define DMI_LAUNCH_FAST(COUNT, SPLIT, CNT)                                                                         \
   tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT><<<persistent_grid((const void*)tsdf_fast_kernel<T, PINHOLE, COUNT, SPLIT>, grid, (unsigned)quota), FT, 0, s>>>( \
-      g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, list, work, quota, d_vol, nbi, nbj, nbk, CNT, firstReservedSm)
+      g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull ? 1 : 0, clsSpare, d_views, masks, list, work, quota, d_vol, nbi, nbj, nbk, CNT)
   if (d_counters) { if (d_depths) DMI_LAUNCH_FAST(true, false, d_counters); else DMI_LAUNCH_FAST(true, true, d_counters); }
   else { if (d_depths) DMI_LAUNCH_FAST(false, false, nullptr); else DMI_LAUNCH_FAST(false, true, nullptr); }
 #undef DMI_LAUNCH_FAST
@@ -911,7 +885,7 @@ size_t tsdf_fast_mask_bytes(const GridParams& g)
 cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
                              ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
-                             FastCounters* d_counters, int quota, int reservedSms, cudaStream_t s)
+                             FastCounters* d_counters, int quota, cudaStream_t s)
 {
   quota = std::max(1, quota);
   const int nbi = (g.Nx + FBI - 1) / FBI, nbj = (g.Ny + FBJ - 1) / FBJ, nbk = (g.nLocal + FM - 1) / FM;
@@ -924,13 +898,13 @@ cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const doub
   const ViewFast* d_views = d_viewScratch;
   if (scalarType == 1)
   {
-    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, quota, reservedSms, s);
-    else launch_variant<double, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, quota, reservedSms, s);
+    if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
+    else launch_variant<double, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
   }
   else
   {
-    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, quota, reservedSms, s);
-    else launch_variant<float, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, quota, reservedSms, s);
+    if (c.pinhole) launch_variant<float, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
+    else launch_variant<float, false>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (float*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
   }
   return cudaGetLastError();
 }

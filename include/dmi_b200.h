@@ -66,9 +66,6 @@ extern "C" {
                                         (default 32; the sharded entry points use 8 so that the NCCL kernels of the
                                         view exchange find a free SM slot quickly) */
 
-#define DMI_OPT_RESERVED_SMS 6       /* tuning: SMs the integration kernel leaves free for kernels of other streams (0 on one
-                                        GPU; the sharded entry points set 24: NCCL's all-gather CTAs need whole SMs) */
-
 typedef struct dmi_ctx dmi_ctx;
 
 /* ---- context ------------------------------------------------------------------------------- */
