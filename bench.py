@@ -506,6 +506,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
         nccl_version = ctx.comm_info()[2]
+        exchange_on = "the copy engines (zero-CTA NCCL communicator, symmetric windows)" if ctx.comm_copy_engines() else "NCCL's kernels"
         ctx.shard_initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
     else:
         ctx.initialize(grid.matrix, grid.point_dims, grid.origin, grid.spacing, rp.thick, rp.rho, rp.eta, rp.delta, (W, H))
@@ -743,8 +744,9 @@ def main():
                                  "note": "fractions of the evaluated pairs (rank 0)"}
         par = "one GPU"
         if world > 1:
-            par = (f"z-layers of 32 cells dealt round-robin over {world} GPUs (dmi_shard_*); prepared views (8 B/pixel lossless split depth + "
-                   f"tile statistics) all-gathered with NCCL {nccl_version} in groups of {max(1, 128 // world) * world} views behind the integration; "
+            par = (f"z-layers of 32 cells dealt round-robin over {world} GPUs (dmi_shard_*); prepared views (8 B/pixel lossless split depth; "
+                   f"the tile statistics are rebuilt locally) all-gathered with NCCL {nccl_version} on {exchange_on} in ramped groups of up to "
+                   f"{max(1, 128 // world) * world} views behind the integration; "
                    "finished layers gathered into rank 0's volume with NCCL send/recv inside the timed region")
         line = {
             "metric": "voxel*view updates/sec", "value": value, "unit": "voxel*views/s", "n_gpus": world,

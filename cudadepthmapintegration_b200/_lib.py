@@ -83,6 +83,7 @@ _PROTOTYPES = {
     "dmi_comm_init": (C.c_int, [_vp, C.c_char_p, _i, _i]),
     "dmi_comm_destroy": (C.c_int, [_vp]),
     "dmi_comm_info": (C.c_int, [_vp, _pi, _pi, _pi]),
+    "dmi_comm_copy_engines": (C.c_int, [_vp]),
     "dmi_shard_initialize": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp]),
     "dmi_shard_view_count": (C.c_int, [_i, _i, _i, _pi]),
     "dmi_shard_view_indices": (C.c_int, [_i, _i, _i, _vp]),

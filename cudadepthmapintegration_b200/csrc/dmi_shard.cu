@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -40,6 +41,13 @@ struct NcclApi
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   decltype(&ncclGetVersion) GetVersion = nullptr;
+  // NCCL >= 2.28 only (optional): communicators that move all-gathers with the copy engines, symmetric windows
+  decltype(&ncclCommInitRankConfig) CommInitRankConfig = nullptr;
+  decltype(&ncclMemAlloc) MemAlloc = nullptr;
+  decltype(&ncclMemFree) MemFree = nullptr;
+  decltype(&ncclCommWindowRegister) CommWindowRegister = nullptr;
+  decltype(&ncclCommWindowDeregister) CommWindowDeregister = nullptr;
+  bool copy_engines() const { return CommInitRankConfig && MemAlloc && MemFree && CommWindowRegister && CommWindowDeregister; }
 };
 
 NcclApi& nccl()
@@ -59,23 +67,92 @@ NcclApi& nccl()
     DMI_NCCL_SYM(Recv, ncclRecv) DMI_NCCL_SYM(GroupStart, ncclGroupStart) DMI_NCCL_SYM(GroupEnd, ncclGroupEnd)
     DMI_NCCL_SYM(GetErrorString, ncclGetErrorString) DMI_NCCL_SYM(GetVersion, ncclGetVersion)
 #undef DMI_NCCL_SYM
+#define DMI_NCCL_OPT(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, #sym));
+    DMI_NCCL_OPT(CommInitRankConfig, ncclCommInitRankConfig) DMI_NCCL_OPT(MemAlloc, ncclMemAlloc) DMI_NCCL_OPT(MemFree, ncclMemFree)
+    DMI_NCCL_OPT(CommWindowRegister, ncclCommWindowRegister) DMI_NCCL_OPT(CommWindowDeregister, ncclCommWindowDeregister)
+#undef DMI_NCCL_OPT
   });
   return api;
 }
 
 static_assert(NCCL_UNIQUE_ID_BYTES == DMI_UNIQUE_ID_BYTES, "dmi_b200.h states the size of ncclUniqueId");
 
+#ifndef NCCL_CTA_POLICY_ZERO
+#define NCCL_CTA_POLICY_ZERO 0x02                          // NCCL 2.28: all-gathers of registered windows run on the copy engines
+#endif
+
+// The view exchange prefers the copy engines (no SM is taken from the integration kernel): that needs NCCL >= 2.28, a
+// communicator created with the zero-CTA policy and group buffers registered as symmetric windows.  DMI_EXCHANGE=sm
+// in the environment keeps NCCL's kernels instead.
+bool want_copy_engines()
+{
+  const char* e = getenv("DMI_EXCHANGE");
+  if (e && !strcmp(e, "sm")) return false;
+  int v = 0;
+  return nccl().err.empty() && nccl().copy_engines() && nccl().GetVersion(&v) == ncclSuccess && v >= 22800;
+}
+
+ncclResult_t comm_init(ncclComm_t* comm, int world, const ncclUniqueId& id, int rank, bool* ce)
+{
+  *ce = false;
+  if (want_copy_engines())
+  {
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.CTAPolicy = NCCL_CTA_POLICY_ZERO;
+    ncclResult_t r = nccl().CommInitRankConfig(comm, world, id, rank, &cfg);
+    if (r == ncclSuccess) *ce = true;
+    return r;
+  }
+  return nccl().CommInitRank(comm, world, id, rank);
+}
+
 constexpr int kRing = 3;          // view-group buffers: one being integrated, one being gathered, one spare
 constexpr int kLayerPlanes = 32;  // z-layer thickness of the sharding = the fast kernel's supertile depth
 
 }  // namespace
 
+// A group buffer: plain device memory, or (copy-engine exchange) NCCL's allocation registered as a symmetric window.
+// ensure() is collective in the second case: every rank calls it with the same size in the same order.
+struct ExchangeBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  ncclWindow_t win = nullptr;
+  bool sym = false;
+  std::string err;
+  bool ensure(size_t bytes, ncclComm_t comm, bool wantSym)
+  {
+    if (bytes <= cap) return true;
+    release(comm);
+    bytes = (bytes + 4095) / 4096 * 4096;
+    if (wantSym)
+    {
+      ncclResult_t r = nccl().MemAlloc(&p, bytes);
+      if (r != ncclSuccess) { p = nullptr; err = std::string("ncclMemAlloc: ") + nccl().GetErrorString(r); return false; }
+      r = nccl().CommWindowRegister(comm, p, bytes, &win, NCCL_WIN_COLL_SYMMETRIC);
+      if (r != ncclSuccess) { win = nullptr; err = std::string("ncclCommWindowRegister: ") + nccl().GetErrorString(r); nccl().MemFree(p); p = nullptr; return false; }
+      sym = true;
+    }
+    else if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; err = cudaGetErrorString(cudaGetLastError()); return false; }
+    cap = bytes;
+    return true;
+  }
+  void release(ncclComm_t comm)
+  {
+    if (p && sym) { if (win) nccl().CommWindowDeregister(comm, win); nccl().MemFree(p); }
+    else if (p) cudaFree(p);
+    p = nullptr; cap = 0; win = nullptr; sym = false;
+  }
+};
+
 struct dmi_shard_state
 {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  bool copy_engines = false;      // the communicator was created with the zero-CTA policy
   cudaStream_t comm_stream = nullptr;
-  DevBuf cls[kRing], lo[kRing], tiles[kRing];
+  ExchangeBuf cls[kRing], lo[kRing];
+  DevBuf tiles[kRing];
   cudaEvent_t ready[kRing] = {}, freed[kRing] = {}, entry = nullptr, staged[2] = {}, stage_free[2] = {};
   bool used[kRing] = {false, false, false}, stage_used[2] = {false, false};
   size_t spare_set_for = 0;       // capacity (floats) for which the spare -1.0f slots were written
@@ -94,7 +171,7 @@ void dmi_host::shard_release(dmi_ctx* ctx)
   if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
   for (int b = 0; b < kRing; b++)
   {
-    s->cls[b].release(); s->lo[b].release(); s->tiles[b].release();
+    s->cls[b].release(s->comm); s->lo[b].release(s->comm); s->tiles[b].release();
     if (s->ready[b]) cudaEventDestroy(s->ready[b]);
     if (s->freed[b]) cudaEventDestroy(s->freed[b]);
   }
@@ -170,8 +247,8 @@ int shard_ensure(dmi_ctx* ctx, const ShardPlan& plan, bool wantLo)
   const size_t clsFloats = cap * npix + 8;               // + the spare -1.0f slot behind the views
   for (int b = 0; b < kRing; b++)
   {
-    DMI_CK(s->cls[b].ensure(clsFloats * 4));
-    if (wantLo) DMI_CK(s->lo[b].ensure(cap * npix * 4));
+    if (!s->cls[b].ensure(clsFloats * 4, s->comm, s->copy_engines)) return ctx->fail(DMI_ERR_OUT_OF_MEMORY, s->cls[b].err);
+    if (wantLo && !s->lo[b].ensure(cap * npix * 4, s->comm, s->copy_engines)) return ctx->fail(DMI_ERR_OUT_OF_MEMORY, s->lo[b].err);
     DMI_CK(s->tiles[b].ensure(cap * tilesPerView * 4));
     if (!s->ready[b])
     {
@@ -216,6 +293,7 @@ int shard_integrate(dmi_ctx* ctx, int nViews, const double* depths, const double
   // the ring buffers may still be read by integration launches of an earlier call on the context's stream
   DMI_CK(cudaEventRecord(s->entry, ctx->stream));
   DMI_CK(cudaStreamWaitEvent(s->comm_stream, s->entry, 0));
+
   EventSpan span = ctx->tsdf_stats.open();
   bool spanOpen = false;
   size_t done = 0;                                        // views of `mine` consumed so far
@@ -320,11 +398,11 @@ int dmi_comm_unique_id(unsigned char id[DMI_UNIQUE_ID_BYTES])
   return DMI_OK;
 }
 
-static int attach_comm(dmi_ctx* ctx, ncclComm_t comm, int rank, int world)
+static int attach_comm(dmi_ctx* ctx, ncclComm_t comm, int rank, int world, bool copyEngines)
 {
   dmi_host::shard_release(ctx);
   dmi_shard_state* s = new dmi_shard_state();
-  s->comm = comm; s->rank = rank; s->world = world;
+  s->comm = comm; s->rank = rank; s->world = world; s->copy_engines = copyEngines;
   ctx->shard = s;
   // CTAs of the persistent integration kernel retire sooner, so that the exchange's kernels find a free SM slot quickly
   if (world > 1 && ctx->opt_quota == 32) ctx->opt_quota = 8;
@@ -342,14 +420,15 @@ int dmi_comm_init(dmi_ctx* ctx, const unsigned char id[DMI_UNIQUE_ID_BYTES], int
   DMI_REQUIRE(world == 1 || id, "null unique id");
   DMI_CK(cudaSetDevice(ctx->device));
   ncclComm_t comm = nullptr;
+  bool ce = false;
   if (world > 1)
   {
     if (!nccl().err.empty()) return ctx->fail(DMI_ERR_CUDA, nccl().err);
     ncclUniqueId u;
     memcpy(&u, id, DMI_UNIQUE_ID_BYTES);
-    DMI_NCCL(nccl().CommInitRank(&comm, world, u, rank));
+    DMI_NCCL(comm_init(&comm, world, u, rank, &ce));
   }
-  return attach_comm(ctx, comm, rank, world);
+  return attach_comm(ctx, comm, rank, world, ce);
 }
 
 int dmi_comm_destroy(dmi_ctx* ctx)
@@ -367,6 +446,13 @@ int dmi_comm_info(dmi_ctx* ctx, int* rank, int* world, int* ncclVersion)
   if (world) *world = ctx->shard->world;
   if (ncclVersion) { *ncclVersion = 0; if (ctx->shard->world > 1 && nccl().GetVersion) nccl().GetVersion(ncclVersion); }
   return DMI_OK;
+}
+
+int dmi_comm_copy_engines(dmi_ctx* ctx)
+{
+  if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
+  if (!ctx->shard) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_comm_init has not been called");
+  return ctx->shard->copy_engines ? 1 : 0;
 }
 
 int dmi_shard_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims[3], const double gridOrig[3],
@@ -563,12 +649,28 @@ int dmi_group_create(const int* devices, int nDevices, dmi_group** out)
     grp->ctx.push_back(c);
   }
   std::vector<ncclComm_t> comms((size_t)nDevices, nullptr);
+  bool ce = false;
   if (nDevices > 1)
   {
-    ncclResult_t r = nccl().err.empty() ? nccl().CommInitAll(comms.data(), nDevices, devices) : ncclSystemError;
+    ncclResult_t r = ncclSystemError;
+    if (nccl().err.empty() && want_copy_engines())
+    {
+      // what ncclCommInitAll does, with a configuration: one unique id, every rank initialised inside one group call
+      ncclUniqueId u;
+      r = nccl().GetUniqueId(&u);
+      if (r == ncclSuccess) r = nccl().GroupStart();
+      for (int q = 0; q < nDevices && r == ncclSuccess; q++)
+      {
+        bool one = false;
+        cudaSetDevice(devices[q]);
+        r = comm_init(&comms[q], nDevices, u, q, &one);
+      }
+      if (r == ncclSuccess) { r = nccl().GroupEnd(); ce = r == ncclSuccess; } else nccl().GroupEnd();
+    }
+    else if (nccl().err.empty()) r = nccl().CommInitAll(comms.data(), nDevices, devices);
     if (r != ncclSuccess)
     {
-      dmi_host::set_create_error(nccl().err.empty() ? std::string("ncclCommInitAll: ") + nccl().GetErrorString(r) : nccl().err);
+      dmi_host::set_create_error(nccl().err.empty() ? std::string("ncclComm init: ") + nccl().GetErrorString(r) : nccl().err);
       for (auto* x : grp->ctx) dmi_destroy(x);
       delete grp;
       return DMI_ERR_CUDA;
@@ -577,7 +679,7 @@ int dmi_group_create(const int* devices, int nDevices, dmi_group** out)
   for (int r = 0; r < nDevices; r++)
   {
     cudaSetDevice(devices[r]);
-    int rc = attach_comm(grp->ctx[r], comms[r], r, nDevices);
+    int rc = attach_comm(grp->ctx[r], comms[r], r, nDevices, ce);
     if (rc != DMI_OK)
     {
       dmi_host::set_create_error(grp->ctx[r]->err);

@@ -377,31 +377,36 @@ __device__ __forceinline__ int nth_set_bit64(unsigned lo, unsigned hi, int n)
   return n < nlo ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - nlo + 1);
 }
 
-// Ordered list of the supertiles some view of the chunk may touch (all of them when useMasks == 0), and the
-// work counter of the persistent integration kernel: work[0] = number of active supertiles, work[1] = 0.
+// List of the supertiles some view of the chunk may touch (all of them when useMasks == 0), and the work counter of the
+// persistent integration kernel: work[0] = number of active supertiles, work[1] = 0.  The list is ordered by the number
+// of views that may touch the supertile, most first (a counting sort over 0..64): the expensive columns near the
+// surface are handed out first and the launch ends on cheap ones, so its tail is short even when a launch holds only a
+// few expensive columns per CTA (a z-layer share of the grid, a short view group).  The order inside a class is
+// whatever the shared-memory atomics give; the result does not depend on it (work items own disjoint voxels).
 __global__ void __launch_bounds__(1024)
 compact_supertiles_kernel(const unsigned* __restrict__ masks, int nst, int useMasks, int* __restrict__ list, int* __restrict__ work)
 {
-  __shared__ int s_warp[32];
-  __shared__ int s_base;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_base = 0;
+  __shared__ int s_bin[kFastChunk + 1];
+  if (threadIdx.x <= kFastChunk) s_bin[threadIdx.x] = 0;
   __syncthreads();
-  for (int b0 = 0; b0 < nst; b0 += 1024)
+  for (int st = threadIdx.x; st < nst; st += 1024)
   {
-    const int st = b0 + threadIdx.x;
-    const bool act = st < nst && (!useMasks || (masks[2 * st] | masks[2 * st + 1]) != 0u);
-    const unsigned bal = __ballot_sync(0xffffffffu, act);
-    if (lane == 0) s_warp[w] = __popc(bal);
-    __syncthreads();
-    int pos = s_base + __popc(bal & ((1u << lane) - 1u));
-    for (int q = 0; q < w; q++) pos += s_warp[q];
-    if (act) list[pos] = st;
-    __syncthreads();
-    if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 32; q++) t += s_warp[q]; s_base += t; }
-    __syncthreads();
+    const int n = useMasks ? __popc(masks[2 * st]) + __popc(masks[2 * st + 1]) : kFastChunk;
+    if (n) atomicAdd(&s_bin[n], 1);
   }
-  if (threadIdx.x == 0) { work[0] = s_base; work[1] = 0; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    int pos = 0;
+    for (int n = kFastChunk; n >= 1; n--) { const int h = s_bin[n]; s_bin[n] = pos; pos += h; }
+    work[0] = pos; work[1] = 0;
+  }
+  __syncthreads();
+  for (int st = threadIdx.x; st < nst; st += 1024)
+  {
+    const int n = useMasks ? __popc(masks[2 * st]) + __popc(masks[2 * st + 1]) : kFastChunk;
+    if (n) list[atomicAdd(&s_bin[n], 1)] = st;
+  }
 }
 
 // One view against the FM voxels of a thread.  INSIDE: every voxel of the brick lands inside the image (mode 2): no bounds

@@ -129,6 +129,13 @@ class Context:
         self._ck(self._lib.dmi_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
         return int(r.value), int(w.value), int(v.value)
 
+    def comm_copy_engines(self):
+        """True when the view exchange runs on the copy engines (see dmi_comm_copy_engines)."""
+        rc = self._lib.dmi_comm_copy_engines(self._h)
+        if rc < 0:
+            self._ck(rc)
+        return bool(rc)
+
     def shard_initialize(self, grid_matrix, grid_dims, grid_orig, grid_spacing, thick, rho, eta, delta, depth_map_dims):
         """dmi_initialize + this rank's z-layers (32 cells each, dealt round-robin)."""
         gm = _f64(grid_matrix).reshape(16)

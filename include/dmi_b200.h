@@ -253,6 +253,10 @@ int dmi_comm_unique_id(unsigned char id[DMI_UNIQUE_ID_BYTES]);
 int dmi_comm_init(dmi_ctx* ctx, const unsigned char id[DMI_UNIQUE_ID_BYTES], int rank, int world);
 int dmi_comm_destroy(dmi_ctx* ctx);
 int dmi_comm_info(dmi_ctx* ctx, int* rank, int* world, int* ncclVersion);
+/* 1 when the view exchange of this communicator runs on the copy engines (NCCL >= 2.28: zero-CTA policy, group buffers
+ * registered as symmetric windows), 0 when NCCL's kernels carry it (older NCCL, or DMI_EXCHANGE=sm in the environment),
+ * negative error code otherwise. */
+int dmi_comm_copy_engines(dmi_ctx* ctx);
 int dmi_shard_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims[3],
                          const double gridOrig[3], const double gridSpacing[3],
                          double rayPotentialThick, double rayPotentialRho, double rayPotentialEta,
