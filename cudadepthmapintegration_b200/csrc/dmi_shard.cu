@@ -150,7 +150,10 @@ struct dmi_shard_state
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   bool copy_engines = false;      // the communicator was created with the zero-CTA policy
-  cudaStream_t comm_stream = nullptr;
+  // comm_stream carries nothing but the all-gathers, so that one group's exchange follows the other without a pause;
+  // the owner-side preparation before it and the rebuilding of the tile statistics after it run on streams of their own
+  cudaStream_t comm_stream = nullptr, prep_stream = nullptr, stats_stream = nullptr;
+  cudaEvent_t prepared[kRing] = {}, gathered[kRing] = {};
   ExchangeBuf cls[kRing], lo[kRing];
   DevBuf tiles[kRing];
   cudaEvent_t ready[kRing] = {}, freed[kRing] = {}, entry = nullptr, staged[2] = {}, stage_free[2] = {};
@@ -168,12 +171,14 @@ void dmi_host::shard_release(dmi_ctx* ctx)
   dmi_shard_state* s = ctx->shard;
   if (!s) return;
   cudaSetDevice(ctx->device);
-  if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+  for (cudaStream_t st : {s->prep_stream, s->comm_stream, s->stats_stream}) if (st) cudaStreamSynchronize(st);
   for (int b = 0; b < kRing; b++)
   {
     s->cls[b].release(s->comm); s->lo[b].release(s->comm); s->tiles[b].release();
     if (s->ready[b]) cudaEventDestroy(s->ready[b]);
     if (s->freed[b]) cudaEventDestroy(s->freed[b]);
+    if (s->prepared[b]) cudaEventDestroy(s->prepared[b]);
+    if (s->gathered[b]) cudaEventDestroy(s->gathered[b]);
   }
   for (int b = 0; b < 2; b++)
   {
@@ -183,7 +188,7 @@ void dmi_host::shard_release(dmi_ctx* ctx)
   if (s->entry) cudaEventDestroy(s->entry);
   s->colors.release();
   if (s->comm && nccl().CommDestroy) nccl().CommDestroy(s->comm);
-  if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+  for (cudaStream_t st : {s->prep_stream, s->comm_stream, s->stats_stream}) if (st) cudaStreamDestroy(st);
   delete s;
   ctx->shard = nullptr;
 }
@@ -254,6 +259,8 @@ int shard_ensure(dmi_ctx* ctx, const ShardPlan& plan, bool wantLo)
     {
       DMI_CK(cudaEventCreateWithFlags(&s->ready[b], cudaEventDisableTiming));
       DMI_CK(cudaEventCreateWithFlags(&s->freed[b], cudaEventDisableTiming));
+      DMI_CK(cudaEventCreateWithFlags(&s->prepared[b], cudaEventDisableTiming));
+      DMI_CK(cudaEventCreateWithFlags(&s->gathered[b], cudaEventDisableTiming));
     }
   }
   for (int b = 0; b < 2; b++)
@@ -267,8 +274,8 @@ int shard_ensure(dmi_ctx* ctx, const ShardPlan& plan, bool wantLo)
   {
     const float minus1 = -1.0f;
     for (int b = 0; b < kRing; b++)
-      DMI_CK(cudaMemcpyAsync((float*)s->cls[b].p + cap * npix, &minus1, 4, cudaMemcpyHostToDevice, s->comm_stream));
-    DMI_CK(cudaStreamSynchronize(s->comm_stream));       // `minus1` lives on this stack frame
+      DMI_CK(cudaMemcpyAsync((float*)s->cls[b].p + cap * npix, &minus1, 4, cudaMemcpyHostToDevice, s->prep_stream));
+    DMI_CK(cudaStreamSynchronize(s->prep_stream));       // `minus1` lives on this stack frame
     s->spare_set_for = cap * npix;
   }
   return DMI_OK;
@@ -292,7 +299,7 @@ int shard_integrate(dmi_ctx* ctx, int nViews, const double* depths, const double
 
   // the ring buffers may still be read by integration launches of an earlier call on the context's stream
   DMI_CK(cudaEventRecord(s->entry, ctx->stream));
-  DMI_CK(cudaStreamWaitEvent(s->comm_stream, s->entry, 0));
+  DMI_CK(cudaStreamWaitEvent(s->prep_stream, s->entry, 0));
 
   EventSpan span = ctx->tsdf_stats.open();
   bool spanOpen = false;
@@ -306,7 +313,7 @@ int shard_integrate(dmi_ctx* ctx, int nViews, const double* depths, const double
     float* cls = (float*)s->cls[slot].p;
     int* lo = (int*)s->lo[slot].p;
     float* tiles = (float*)s->tiles[slot].p;
-    if (s->used[slot]) DMI_CK(cudaStreamWaitEvent(s->comm_stream, s->freed[slot], 0));
+    if (s->used[slot]) DMI_CK(cudaStreamWaitEvent(s->prep_stream, s->freed[slot], 0));
     if (mineN > 0)
     {
       const double* d = depths + npix * done;
@@ -321,7 +328,7 @@ int shard_integrate(dmi_ctx* ctx, int nViews, const double* depths, const double
         DMI_CK(cudaMemcpyAsync(ctx->stage_depth[st].p, d, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         if (cost) DMI_CK(cudaMemcpyAsync(ctx->stage_cost[st].p, c, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         DMI_CK(cudaEventRecord(s->staged[st], ctx->copy_stream));
-        DMI_CK(cudaStreamWaitEvent(s->comm_stream, s->staged[st], 0));
+        DMI_CK(cudaStreamWaitEvent(s->prep_stream, s->staged[st], 0));
         d = (const double*)ctx->stage_depth[st].p;
         c = cost ? (const double*)ctx->stage_cost[st].p : nullptr;
       }
@@ -329,17 +336,20 @@ int shard_integrate(dmi_ctx* ctx, int nViews, const double* depths, const double
       const size_t seg = (size_t)(a - g0);
       // (with several ranks the tile statistics are not exchanged: every rank rebuilds them from the classification images)
       DMI_CK(dmi::launch_prepare_views(d, c, thr, mineN, g.W, g.H, cls + seg * npix, lo + seg * npix, -1,
-                                       tiles + seg * tilesPerView, s->comm_stream, s->world == 1));
+                                       tiles + seg * tilesPerView, s->prep_stream, s->world == 1));
       ctx->total_launches += s->world == 1 ? 1 + dmi::tile_pyramid_layout(g.W, g.H).nLevels : 1;
       if (fromHost)
       {
-        DMI_CK(cudaEventRecord(s->stage_free[gi & 1], s->comm_stream));
+        DMI_CK(cudaEventRecord(s->stage_free[gi & 1], s->prep_stream));
         s->stage_used[gi & 1] = true;
       }
       done += (size_t)mineN;
     }
+    DMI_CK(cudaEventRecord(s->prepared[slot], s->prep_stream));
+    cudaEvent_t ready = s->prepared[slot];
     if (s->world > 1)
     {
+      DMI_CK(cudaStreamWaitEvent(s->comm_stream, s->prepared[slot], 0));
       // in place: rank r's segment starts r * pg views into each array (the last group is padded to pg * world views)
       const size_t r = (size_t)s->rank * pg;
       DMI_NCCL(nccl().GroupStart());
@@ -347,11 +357,14 @@ int shard_integrate(dmi_ctx* ctx, int nViews, const double* depths, const double
       DMI_NCCL(nccl().AllGather(lo + r * npix, lo, (size_t)pg * npix, ncclInt32, s->comm, s->comm_stream));
       DMI_NCCL(nccl().GroupEnd());
       // 8 bytes per pixel travelled; the tile statistics (19 % more) are rebuilt here from the classification images
-      DMI_CK(dmi::launch_tile_stats_from_cls(cls, g1 - g0, g.W, g.H, tiles, s->comm_stream));
+      DMI_CK(cudaEventRecord(s->gathered[slot], s->comm_stream));
+      DMI_CK(cudaStreamWaitEvent(s->stats_stream, s->gathered[slot], 0));
+      DMI_CK(dmi::launch_tile_stats_from_cls(cls, g1 - g0, g.W, g.H, tiles, s->stats_stream));
       ctx->total_launches += 1 + dmi::tile_pyramid_layout(g.W, g.H).nLevels;
+      DMI_CK(cudaEventRecord(s->ready[slot], s->stats_stream));
+      ready = s->ready[slot];
     }
-    DMI_CK(cudaEventRecord(s->ready[slot], s->comm_stream));
-    DMI_CK(cudaStreamWaitEvent(ctx->stream, s->ready[slot], 0));
+    DMI_CK(cudaStreamWaitEvent(ctx->stream, ready, 0));
     if (haveWork)
     {
       if (!spanOpen) { DMI_CK(cudaEventRecord(span.a, ctx->stream)); spanOpen = true; }
@@ -410,6 +423,8 @@ static int attach_comm(dmi_ctx* ctx, ncclComm_t comm, int rank, int world, bool 
   DMI_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   // high priority: the exchange's few CTAs must not queue behind the integration kernel's
   DMI_CK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, hi));
+  DMI_CK(cudaStreamCreateWithPriority(&s->prep_stream, cudaStreamNonBlocking, hi));
+  DMI_CK(cudaStreamCreateWithPriority(&s->stats_stream, cudaStreamNonBlocking, hi));
   return DMI_OK;
 }
 
