@@ -86,13 +86,6 @@ int dmi_destroy(dmi_ctx* ctx)
   ctx->filtered.release();
   ctx->counters.release();
   ctx->cls.release(); ctx->tiles.release(); ctx->viewscratch.release(); ctx->maskscratch.release();
-  if (ctx->param_stream) { cudaStreamSynchronize(ctx->param_stream); cudaStreamDestroy(ctx->param_stream); }
-  for (int q = 0; q < dmi_ctx::kViewRing; q++)
-  {
-    if (ctx->view_up[q]) cudaEventDestroy(ctx->view_up[q]);
-    if (ctx->view_free[q]) cudaEventDestroy(ctx->view_free[q]);
-  }
-  if (ctx->h_views) cudaFreeHost(ctx->h_views);
   ctx->c_xyz.release(); ctx->c_colors.release(); ctx->c_mats.release();
   ctx->c_mean.release(); ctx->c_median.release(); ctx->c_nb.release(); ctx->c_sort.release();
   ctx->tsdf_stats.destroy(); ctx->color_stats.destroy();
@@ -381,54 +374,29 @@ int dmi_host::integrate_fast_prepared(dmi_ctx* ctx, int nViews, const double* d_
     DMI_REQUIRE(hi <= 2147483647ll && lo >= -2147483647ll,
                 "the spare classification slot must lie within 2^31 floats of every view of the call: split the call");
   }
-  constexpr int R = dmi_ctx::kViewRing;
-  DMI_CK(ctx->viewscratch.ensure(sizeof(dmi::FastViews) * R));
+  DMI_CK(ctx->viewscratch.ensure(sizeof(dmi::ViewFast) * dmi::kFastChunk));
   DMI_CK(ctx->maskscratch.ensure(dmi::tsdf_fast_mask_bytes(g)));
-  if (!ctx->h_views)
-  {
-    DMI_CK(cudaMallocHost((void**)&ctx->h_views, sizeof(dmi::FastViews) * R));
-    DMI_CK(cudaStreamCreateWithFlags(&ctx->param_stream, cudaStreamNonBlocking));
-    for (int q = 0; q < R; q++)
-    {
-      DMI_CK(cudaEventCreateWithFlags(&ctx->view_up[q], cudaEventDisableTiming));
-      DMI_CK(cudaEventCreateWithFlags(&ctx->view_free[q], cudaEventDisableTiming));
-    }
-  }
-  dmi::FastHead head{};
-  dmi::fill_fast_chunk_constants(g, &head);
+  dmi::FastChunk* c = &ctx->fast_chunk;
+  dmi::fill_fast_chunk_constants(g, c);
   for (int v0 = 0; v0 < nViews; v0 += chunk)
   {
-    const int slot = (int)(ctx->view_seq++ % R);
-    dmi::FastViews* hv = ctx->h_views + slot;
-    dmi::FastViews* dv = (dmi::FastViews*)ctx->viewscratch.p + slot;
-    if (ctx->view_used[slot])
-    {
-      DMI_CK(cudaEventSynchronize(ctx->view_up[slot]));                        // the pinned slot has been read (R chunks ago)
-      DMI_CK(cudaStreamWaitEvent(ctx->param_stream, ctx->view_free[slot], 0)); // its device slot's launch is over
-    }
-    head.n = std::min(chunk, nViews - v0);
-    head.pinhole = 1;
-    for (int q = 0; q < head.n; q++)
+    c->n = std::min(chunk, nViews - v0);
+    c->pinhole = 1;
+    for (int q = 0; q < c->n; q++)
     {
       const double* k16 = K + 16 * (size_t)(v0 + q);
       const double* rt16 = RT + 16 * (size_t)(v0 + q);
-      dmi::compose_fast_view(g, k16, rt16, head.cxc, head.cyc, &hv->v[q]);
-      memcpy(hv->e[q].RT, rt16, sizeof(double) * 12);
-      memcpy(hv->e[q].K, k16, sizeof(double) * 12);
-      if (!(k16[8] == 0.0 && k16[9] == 0.0 && k16[10] == 1.0 && k16[11] == 0.0)) head.pinhole = 0;
+      dmi::compose_fast_view(g, k16, rt16, c->cxc, c->cyc, &c->v[q]);
+      memcpy(c->e[q].RT, rt16, sizeof(double) * 12);
+      memcpy(c->e[q].K, k16, sizeof(double) * 12);
+      if (!(k16[8] == 0.0 && k16[9] == 0.0 && k16[10] == 1.0 && k16[11] == 0.0)) c->pinhole = 0;
     }
-    DMI_CK(cudaMemcpyAsync(dv->v, hv->v, sizeof(dmi::ViewFast) * head.n, cudaMemcpyHostToDevice, ctx->param_stream));
-    DMI_CK(cudaMemcpyAsync(dv->e, hv->e, sizeof(dmi::ViewExact) * head.n, cudaMemcpyHostToDevice, ctx->param_stream));
-    DMI_CK(cudaEventRecord(ctx->view_up[slot], ctx->param_stream));
-    DMI_CK(cudaStreamWaitEvent(ctx->stream, ctx->view_up[slot], 0));
-    DMI_CK(dmi::launch_tsdf_fast(g, head, d_depths ? d_depths + npix * v0 : nullptr, d_lo ? d_lo + npix * v0 : nullptr, d_cls + npix * v0, clsSpare - (long long)(npix * (size_t)v0),
-                                 d_tiles + tilesPerView * v0, ctx->opt_cull, dv,
+    DMI_CK(dmi::launch_tsdf_fast(g, *c, d_depths ? d_depths + npix * v0 : nullptr, d_lo ? d_lo + npix * v0 : nullptr, d_cls + npix * v0, clsSpare - (long long)(npix * (size_t)v0),
+                                 d_tiles + tilesPerView * v0, ctx->opt_cull, (dmi::ViewFast*)ctx->viewscratch.p,
                                  (unsigned*)ctx->maskscratch.p, ctx->vol.p, ctx->vol_type,
                                  ctx->counters_on ? (dmi::FastCounters*)ctx->counters.p : nullptr, ctx->opt_quota, ctx->stream));
-    DMI_CK(cudaEventRecord(ctx->view_free[slot], ctx->stream));
-    ctx->view_used[slot] = true;
     ctx->tsdf_stats.launches++;
-    ctx->total_launches += ctx->opt_cull ? 4 : 3;         // view flags, supertile culling, compaction, integration
+    ctx->total_launches += ctx->opt_cull ? 4 : 3;         // view staging, supertile culling, compaction, integration
   }
   return DMI_OK;
 }

@@ -81,15 +81,8 @@ struct dmi_ctx
   KernelStats tsdf_stats, color_stats;
   long long opt_kernel = DMI_TSDF_KERNEL_AUTO, opt_chunk = 0;
   long long total_launches = 0;
-  // per-view records of the fast path's launches: composed into a pinned slot, uploaded on `param_stream` ahead of the
-  // launch that reads them (a ring, so that neither the host nor the upload waits for the launch before)
-  static constexpr int kViewRing = 4;
-  dmi::FastViews* h_views = nullptr;                       // pinned host memory, kViewRing slots
-  cudaStream_t param_stream = nullptr;
-  cudaEvent_t view_up[kViewRing] = {}, view_free[kViewRing] = {};
-  bool view_used[kViewRing] = {};
-  unsigned long long view_seq = 0;
-  DevBuf counters, cls, tiles, viewscratch, maskscratch;   // viewscratch: kViewRing FastViews
+  dmi::FastChunk fast_chunk{};
+  DevBuf counters, cls, tiles, viewscratch, maskscratch;
   bool counters_on = false;
   bool opt_cull = true;
   int opt_quota = 32;

@@ -63,11 +63,8 @@ struct ViewFast
   float pad[3];
 };
 
-constexpr int kFastChunk = 64;    // views per launch
-// What a launch of the fast path is told about its chunk of views: the scalars travel as kernel parameters, the per-view
-// records (64 * (248 + 192) B = 28 KB) live in device memory -- as kernel parameters they cost ~0.6 ms of idle GPU per
-// launch sequence (the driver's large-parameter path), a third of a launch on a z-layer share of the grid.
-struct FastHead
+constexpr int kFastChunk = 64;    // views per launch: 64 * (248 + 192) B = 28 KB of kernel parameters
+struct FastChunk
 {
   int n;
   int cxc, cyc;                   // integer pixel offsets removed from the numerators
@@ -76,11 +73,6 @@ struct FastHead
   float k3;                       // E = k3 * ((|b| + 3 l) + U1 * (|bz| + 3 lz))
   float kq;                       // T = 0.5 - U1 * kq - 2^-20
   float delta_up;                 // float >= Delta * (1 + 2^-20)
-  const ViewFast* v;              // device memory: n records (pad[0] = the view's "has a fully valid tile" flag)
-  const ViewExact* e;             // device memory: n records, for the exact tier
-};
-struct FastViews                  // the per-view records of one chunk, as composed on the host and uploaded
-{
   ViewFast v[kFastChunk];
   ViewExact e[kFastChunk];
 };
@@ -134,14 +126,13 @@ cudaError_t launch_prepare_views(const double* d_depths, const double* d_cost, d
 cudaError_t launch_tile_stats_from_cls(const float* d_cls, int nViews, int W, int H, float* d_tileStats, cudaStream_t s);
 // d_cls[clsSpare] (an index relative to d_cls) must hold -1.0f: launch_prepare_views(n views) writes it at n*W*H
 // d_depths null: the double depths are rebuilt from (d_cls, d_lo)
-// d_views: the chunk's FastViews in device memory (uploaded by the caller, stream-ordered before this call)
-cudaError_t launch_tsdf_fast(const GridParams& g, FastHead c, const double* d_depths, const int* d_lo,
+cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
-                             FastViews* d_views, unsigned* d_maskScratch, void* d_vol, int scalarType,
+                             ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
                              FastCounters* d_counters, int quota, cudaStream_t s);
 size_t tsdf_fast_mask_bytes(const GridParams& g);   // size of d_maskScratch: per supertile a 64-bit view mask + a list entry, + work counters
 void compose_fast_view(const GridParams& g, const double* K16, const double* RT16, int cxc, int cyc, ViewFast* out);
-void fill_fast_chunk_constants(const GridParams& g, FastHead* c);
+void fill_fast_chunk_constants(const GridParams& g, FastChunk* c);
 
 cudaError_t launch_tsdf_exact(const GridParams& g, const ExactChunk& c, const double* d_depths,
                               void* d_vol, int scalarType, cudaStream_t s);

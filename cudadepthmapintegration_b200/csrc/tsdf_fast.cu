@@ -37,9 +37,6 @@
 #include <cmath>
 #include <climits>
 #include <algorithm>
-#include <map>
-#include <mutex>
-#include <utility>
 
 #ifndef DMI_FAST_CTAS
 #define DMI_FAST_CTAS 6          // CTAs of the integration kernel per SM (register cap 65536 / (128 * CTAs)); measured on config 5,
@@ -208,7 +205,7 @@ struct BrickBox { bool valid, inside; float ux, uy; int tx0, tx1, ty0, ty1; };
 // the local terms.  Returns false when the box cannot be trusted (too close to the camera plane).
 // Margins: 1.5 px + the FP32 evaluation error (<= 0.25 px inside the image by the E*r test,
 // proportional to |u| outside).
-__device__ __forceinline__ bool brick_box(const ViewFast& V, const FastHead& c, float fbx, float fby, float fbz,
+__device__ __forceinline__ bool brick_box(const ViewFast& V, const FastChunk& c, float fbx, float fby, float fbz,
                                           float ei, float ej, float ek, float lx, float ly, float lz,
                                           float zlo, int W, int H, BrickBox& o, bool& outside)
 {
@@ -290,7 +287,7 @@ __device__ __forceinline__ float footprint_bad(const TilePyramid& pyr, const flo
 struct BoxEval { bool keep; int front, mode; float fbx, fby, fbz, fbc, Ux, Uy, czmaxabs, rmax; };
 
 template <bool PINHOLE>
-__device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastHead& c, const TilePyramid& pyr,
+__device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastChunk& c, const TilePyramid& pyr,
                                             const float* __restrict__ td, int i0, int j0, int k0,
                                             float ei, float ej, float ek, float lx, float ly, float lz, float lc,
                                             int W, int H, bool cull)
@@ -349,7 +346,7 @@ __device__ __forceinline__ BoxEval eval_box(const ViewFast& V, const FastHead& c
 // may contribute to supertile st.  A brick only examines the views its supertile kept.
 template <bool PINHOLE>
 __global__ void __launch_bounds__(256)
-supertile_cull_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastHead c,
+supertile_cull_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
                       const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr,
                       const ViewFast* __restrict__ gviews, int nbi, int nbj, int nbk, unsigned* __restrict__ masks, int nst)
 {
@@ -417,7 +414,7 @@ compact_supertiles_kernel(const unsigned* __restrict__ masks, int nst, int useMa
 // so phase C only looks at the pixel's validity.
 template <typename T, bool PINHOLE, bool COUNT, bool SPLIT, bool INSIDE>
 __device__ __forceinline__ void
-integrate_view(const GridParams& g, const FastHead& c, const ViewSm& S, const ViewConst& VC, const double* __restrict__ depths,
+integrate_view(const GridParams& g, const FastChunk& c, const ViewSm& S, const ViewConst& VC, const double* __restrict__ depths,
                const int* __restrict__ lo, const float* __restrict__ cls, size_t npix, float fli, float flj,
                double di, double dj, double dk0, int i, int j, int k0, T nerT, bool front2, T (&acc)[FM], unsigned long long (&cnt)[10])
 {
@@ -633,7 +630,7 @@ constexpr int kColBricks = FSK;   // bricks of one work item: a column of the su
 // image and the residual image `lo` (split_decode), bit for bit.
 template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
 __device__ __forceinline__ void
-fast_column(const GridParams& g, const FastHead& c, const double* __restrict__ depths, const int* __restrict__ lo,
+fast_column(const GridParams& g, const FastChunk& c, const double* __restrict__ depths, const int* __restrict__ lo,
             const float* __restrict__ cls, const float* __restrict__ tileDmax, const TilePyramid& pyr, int cull,
             long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
             T* __restrict__ vol, int nbi, int nbj, int nbk, FastCounters* counters, unsigned st, unsigned col,
@@ -795,7 +792,7 @@ fast_column(const GridParams& g, const FastHead& c, const double* __restrict__ d
 // within a fraction of a millisecond instead of waiting for the whole launch (DMI_OPT_BRICK_QUOTA, in bricks).
 template <typename T, bool PINHOLE, bool COUNT, bool SPLIT>
 __global__ void __launch_bounds__(FT, DMI_FAST_CTAS)
-tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastHead c,
+tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ FastChunk c,
                  const double* __restrict__ depths, const int* __restrict__ lo, const float* __restrict__ cls,
                  const float* __restrict__ tileDmax, const __grid_constant__ TilePyramid pyr, int cull,
                  long long clsSpare, const ViewFast* __restrict__ gviews, const unsigned* __restrict__ stmasks,
@@ -836,42 +833,32 @@ tsdf_fast_kernel(const __grid_constant__ GridParams g, const __grid_constant__ F
   }
 }
 
-// pad[0] of each uploaded view = the view's "has a fully valid tile" flag from its tile statistics: views
+// pad[0] of each staged view = the view's "has a fully valid tile" flag from its tile statistics: views
 // without one (salt-and-pepper holes) skip the free-space test of eval_box altogether.
-__global__ void __launch_bounds__(64) view_flags_kernel(int n, ViewFast* __restrict__ dst, const float* __restrict__ tiles,
-                                                        int perView, int flagOff)
+__global__ void __launch_bounds__(256) stage_views_kernel(const __grid_constant__ FastChunk c, ViewFast* __restrict__ dst,
+                                                          const float* __restrict__ tiles, int perView, int flagOff)
 {
-  if ((int)threadIdx.x < n) dst[threadIdx.x].pad[0] = tiles[(size_t)threadIdx.x * perView + flagOff];
+  const unsigned* src = reinterpret_cast<const unsigned*>(c.v);
+  unsigned* d = reinterpret_cast<unsigned*>(dst);
+  const int words = (int)(sizeof(ViewFast) / 4) * c.n;
+  for (int q = threadIdx.x; q < words; q += blockDim.x) d[q] = src[q];
+  __syncthreads();
+  if ((int)threadIdx.x < c.n) dst[threadIdx.x].pad[0] = tiles[(size_t)threadIdx.x * perView + flagOff];
 }
 
 // Enough CTAs to take every work item at `quota` each, at least as many as are resident at once on this device
 static unsigned persistent_grid(const void* kernel, unsigned bricks, unsigned quota)
 {
-  // (per kernel variant and device: the occupancy query costs tens of microseconds of host time per call)
-  static std::mutex mu;
-  static std::map<std::pair<const void*, int>, unsigned> cache;
-  int dev = 0;
+  int dev = 0, sms = 0, perSm = 0;
   cudaGetDevice(&dev);
-  unsigned resident = 0;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = cache.find({kernel, dev});
-    if (it != cache.end()) resident = it->second;
-  }
-  if (!resident)
-  {
-    int sms = 0, perSm = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, FT, 0);
-    resident = (unsigned)(std::max(sms, 1) * std::max(perSm, 1));
-    std::lock_guard<std::mutex> lock(mu);
-    cache[{kernel, dev}] = resident;
-  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, FT, 0);
+  const unsigned resident = (unsigned)(std::max(sms, 1) * std::max(perSm, 1));
   return std::max(1u, std::min(bricks, std::max(resident, (bricks + quota - 1) / quota)));
 }
 
 template <typename T, bool PINHOLE>
-static void launch_variant(unsigned grid, const GridParams& g, const FastHead& c, const double* d_depths, const int* d_lo,
+static void launch_variant(unsigned grid, const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                            const float* d_cls, const float* d_tileDmax, const TilePyramid& pyr, bool cull,
                            long long clsSpare, const ViewFast* d_views, unsigned* d_masks, T* d_vol, int nbi, int nbj,
                            int nbk, FastCounters* d_counters, int quota, cudaStream_t s)
@@ -900,9 +887,9 @@ size_t tsdf_fast_mask_bytes(const GridParams& g)
   return nsi * nsj * nsk * 12 + 16;       // masks (2 words), the active list (1 word) per supertile + the work counters
 }
 
-cudaError_t launch_tsdf_fast(const GridParams& g, FastHead c, const double* d_depths, const int* d_lo,
+cudaError_t launch_tsdf_fast(const GridParams& g, const FastChunk& c, const double* d_depths, const int* d_lo,
                              const float* d_cls, long long clsSpare, const float* d_tileDmax, bool cull,
-                             FastViews* d_fastViews, unsigned* d_maskScratch, void* d_vol, int scalarType,
+                             ViewFast* d_viewScratch, unsigned* d_maskScratch, void* d_vol, int scalarType,
                              FastCounters* d_counters, int quota, cudaStream_t s)
 {
   quota = std::max(1, quota);
@@ -911,10 +898,9 @@ cudaError_t launch_tsdf_fast(const GridParams& g, FastHead c, const double* d_de
   const unsigned nsi = (nbi + FSI - 1) / FSI, nsj = (nbj + FSJ - 1) / FSJ, nsk = (nbk + FSK - 1) / FSK;
   const unsigned grid = nsi * nsj * nsk * (FSI * FSJ * FSK);
   const TilePyramid pyr = tile_pyramid_layout(g.W, g.H);
-  c.v = d_fastViews->v;
-  c.e = d_fastViews->e;
-  view_flags_kernel<<<1, 64, 0, s>>>(c.n, d_fastViews->v, d_tileDmax, pyr.perView, pyr.flagOff);
-  const ViewFast* d_views = c.v;
+  // stream-ordered copy of the views from the parameter space to global memory, for the pre-pass
+  stage_views_kernel<<<1, 256, 0, s>>>(c, d_viewScratch, d_tileDmax, pyr.perView, pyr.flagOff);
+  const ViewFast* d_views = d_viewScratch;
   if (scalarType == 1)
   {
     if (c.pinhole) launch_variant<double, true>(grid, g, c, d_depths, d_lo, d_cls, d_tileDmax, pyr, cull, clsSpare, d_views, d_maskScratch, (double*)d_vol, nbi, nbj, nbk, d_counters, quota, s);
@@ -1189,7 +1175,7 @@ static float up(double x)      // a float >= x (x >= 0)
   return f;
 }
 
-void fill_fast_chunk_constants(const GridParams& g, FastHead* c)
+void fill_fast_chunk_constants(const GridParams& g, FastChunk* c)
 {
   c->cxc = g.W / 2;
   c->cyc = g.H / 2;
