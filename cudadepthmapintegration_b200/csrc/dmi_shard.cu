@@ -129,8 +129,10 @@ struct ExchangeBuf
     {
       ncclResult_t r = nccl().MemAlloc(&p, bytes);
       if (r != ncclSuccess) { p = nullptr; err = std::string("ncclMemAlloc: ") + nccl().GetErrorString(r); return false; }
+      // best effort: without a window (no symmetric-memory support on this system) the buffer is still valid device
+      // memory and the all-gather falls back to NCCL's kernels
       r = nccl().CommWindowRegister(comm, p, bytes, &win, NCCL_WIN_COLL_SYMMETRIC);
-      if (r != ncclSuccess) { win = nullptr; err = std::string("ncclCommWindowRegister: ") + nccl().GetErrorString(r); nccl().MemFree(p); p = nullptr; return false; }
+      if (r != ncclSuccess) win = nullptr;
       sym = true;
     }
     else if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; err = cudaGetErrorString(cudaGetLastError()); return false; }
@@ -467,7 +469,9 @@ int dmi_comm_copy_engines(dmi_ctx* ctx)
 {
   if (!ctx) return DMI_ERR_INVALID_ARGUMENT;
   if (!ctx->shard) return ctx->fail(DMI_ERR_NOT_INITIALIZED, "dmi_comm_init has not been called");
-  return ctx->shard->copy_engines ? 1 : 0;
+  const dmi_shard_state* s = ctx->shard;
+  // (once the group buffers exist: only if their windows could be registered)
+  return s->copy_engines && !(s->cls[0].p && !s->cls[0].win) ? 1 : 0;
 }
 
 int dmi_shard_initialize(dmi_ctx* ctx, const double gridMatrix[16], const int gridDims[3], const double gridOrig[3],
