@@ -101,7 +101,8 @@ ncclResult_t comm_init(ncclComm_t* comm, int world, const ncclUniqueId& id, int 
     cfg.CTAPolicy = NCCL_CTA_POLICY_ZERO;
     ncclResult_t r = nccl().CommInitRankConfig(comm, world, id, rank, &cfg);
     if (r == ncclSuccess) *ce = true;
-    return r;
+    // a library that rejects the configuration does so before any rendezvous: the plain communicator still works
+    if (r != ncclInvalidArgument) return r;
   }
   return nccl().CommInitRank(comm, world, id, rank);
 }
