@@ -276,7 +276,7 @@ int dmi_shard_colorize_device(dmi_ctx* ctx, size_t nMyPoints, const void* d_myXy
                               uint8_t* d_mean, uint8_t* d_median, int32_t* d_nbProjected);
 
 /* Single-process form: one object drives all the GPUs listed (one host thread per GPU inside each call, NCCL
- * communicators from ncclCommInitAll).  This is the multi-GPU counterpart of the reference's two entry points:
+ * communicators created in one NCCL group call, like ncclCommInitAll).  This is the multi-GPU counterpart of the reference's two entry points:
  *   dmi_group_initialize          CudaInitialize (CudaReconstruction.cu:269-298)
  *   dmi_group_process_depth_maps  ProcessDepthMap<T> (:302-386): host pointers, ALL views, io_scalar = the whole grid
  *                                 (accumulated onto); each GPU uploads only the views and the layers it owns and
